@@ -1,0 +1,135 @@
+/* npe_pfn_b200 — C ABI of the B200-native (sm_100a) in-context engine.
+ *
+ * This is the boundary the reference's hot path binds to.  The reference
+ * (`/root/reference/npe_pfn/npe_pfn.py`) reaches its arithmetic through five
+ * calls into the third-party `tabpfn` estimator:
+ *
+ *   TabPFNRegressor(**kw)                              npe_pfn.py:48, 69     -> pfn_ctx_create
+ *   model.fit(joint[:, :dx+d], joint[:, dx+d])         npe_pfn.py:140,215,502 -> pfn_prefill
+ *   model.predict(X, output_type="full", quantiles=[]) npe_pfn.py:143-145,217-219,505-507
+ *                                                      -> pfn_forward_logits
+ *   criterion.sample(logits)                           npe_pfn.py:146, 220   -> pfn_head_sample / pfn_sample (fused)
+ *   criterion(logits, y)                               npe_pfn.py:149-151,226-228,510-512
+ *                                                      -> pfn_head_nll / pfn_logprob (fused)
+ *   accept_reject_sample / _within_support             accept_reject_sampler.py:54-62, npe_pfn.py:581-600
+ *                                                      -> pfn_accept_compact
+ *
+ * Conventions
+ *   - plain C types only; every data pointer is a DEVICE pointer owned by the
+ *     caller (e.g. a torch tensor's data_ptr) unless marked "host";
+ *   - the library owns the handle, its bf16 weight copies, per-slot K/V caches
+ *     and a grow-only workspace;
+ *   - all work is enqueued on the caller's `stream` (a cudaStream_t passed as
+ *     void*); no host synchronisation except where a count is returned through
+ *     a host pointer and in workspace growth;
+ *   - every function returns 0 on success, non-zero on failure;
+ *     `pfn_last_error()` returns a thread-local message.
+ *   - a "slot" holds everything `fit` produces for one (context, dimension):
+ *     encoder statistics, y mean/std, renormalised bucket borders and the
+ *     head-0 K/V cache of the context rows for all layers.
+ */
+#ifndef NPE_PFN_B200_H
+#define NPE_PFN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PFN_ABI_VERSION 1
+
+typedef struct pfn_ctx pfn_ctx; /* opaque */
+
+typedef struct pfn_model_config {
+    int32_t emsize;       /* 192 */
+    int32_t nhead;        /* 6   */
+    int32_t nlayers;      /* 12  */
+    int32_t nhid;         /* 768 */
+    int32_t num_buckets;  /* 5000 */
+    int32_t max_groups;   /* rows of pos_emb in the blob */
+    int32_t max_slots;    /* number of (context, dimension) caches kept */
+    int32_t chunk_rows;   /* test rows processed per pass (0 = default) */
+    float ln_eps;         /* 1e-5 */
+    float softmax_temperature; /* logits are divided by this (0.9) */
+} pfn_model_config;
+
+int pfn_abi_version(void);
+const char* pfn_last_error(void);
+
+/* `weights` = flat fp32 blob on the device in the order of
+ * npe_pfn_b200/weights.py::blob_layout; copied/converted, caller may free it. */
+int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_floats, int device,
+                   void* stream, pfn_ctx** out);
+int pfn_ctx_destroy(pfn_ctx* ctx);
+/* runtime switches (no reference counterpart): "attn_impl" 0 = warp-level mma.sync item attention,
+ * 1 = tcgen05/TMEM item attention (default); "chunk_rows" = test rows per pass; "time_kernels" 1 = record a
+ * CUDA event pair around every attention / GEMM launch on its stream (read back with pfn_kernel_times). */
+int pfn_set_option(pfn_ctx* ctx, const char* key, int64_t value);
+
+/* fit: context rows X[N, F] (row stride ldx floats), raw targets y[N].
+ * Standardises y, computes encoder statistics, runs the context through all
+ * layers and stores the head-0 K/V cache in `slot`. */
+int pfn_prefill(pfn_ctx* ctx, int slot, const float* X, int64_t ldx, const float* y, int64_t N, int F,
+                void* stream);
+
+/* predict(output_type="full"): raw decoder logits / temperature for M test rows.
+ * X[M, F] with row stride ldx; out[M, num_buckets] with row stride ld_out. */
+int pfn_forward_logits(pfn_ctx* ctx, int slot, const float* X, int64_t ldx, int64_t M, float* out,
+                       int64_t ld_out, void* stream);
+
+/* Head on materialised logits (what `criterion.sample` / `criterion(logits, y)` do).
+ * uniforms == NULL -> Philox4x32-10(seed; counter = (row0 + r, offset)).
+ * Any of out_bin / out_u / out_logp may be NULL.  out_theta[r * ld_theta].
+ * out_logp (if given) receives log p(theta_r) with -inf replaced by log(eps);
+ * when `accumulate` != 0 it is added to the existing value. */
+int pfn_head_sample(pfn_ctx* ctx, int slot, const float* logits, int64_t ld_logits, int64_t M,
+                    const float* uniforms, uint64_t seed, uint64_t row0, uint64_t offset,
+                    float* out_theta, int64_t ld_theta, int32_t* out_bin, float* out_u,
+                    float* out_logp, float eps, int accumulate, void* stream);
+/* out_nll[r] = -log p(y_r) (may be +inf).  If out_logp != NULL it receives the
+ * clamped log-prob as in pfn_head_sample. */
+int pfn_head_nll(pfn_ctx* ctx, int slot, const float* logits, int64_t ld_logits, int64_t M,
+                 const float* y, int64_t ld_y, float* out_nll, float* out_logp, float eps,
+                 int accumulate, void* stream);
+
+/* Fused autoregressive step: forward + head, logits never leave the library.
+ * pfn_sample writes theta_d for each row (e.g. straight into column dx+d of
+ * the caller's joint matrix: out_theta = joint + dx + d, ld_theta = ld of joint). */
+int pfn_sample(pfn_ctx* ctx, int slot, const float* X, int64_t ldx, int64_t M, const float* uniforms,
+               uint64_t seed, uint64_t row0, uint64_t offset, float* out_theta, int64_t ld_theta,
+               int32_t* out_bin, float* out_logp, float eps, int accumulate, void* stream);
+int pfn_logprob(pfn_ctx* ctx, int slot, const float* X, int64_t ldx, int64_t M, const float* y,
+                int64_t ld_y, float* out_logp, float eps, int accumulate, void* stream);
+
+/* Support check + ordered stream compaction (accept_reject_sampler.py:54-62).
+ * Row r is accepted iff lo[j] <= theta[r, j] <= hi[j] for all j (lo/hi may be
+ * +-inf; NULL = unbounded) and (mask == NULL or mask[r] != 0) and all finite.
+ * out_idx[0..count) = accepted row indices in increasing order; out_rows (may
+ * be NULL) receives the accepted rows packed [count, dim] (row stride dim);
+ * out_count is a DEVICE int64.  No host sync. */
+int pfn_accept_compact(pfn_ctx* ctx, const float* theta, int64_t ld, int64_t M, int dim, const float* lo,
+                       const float* hi, const uint8_t* mask, int64_t* out_idx, float* out_rows,
+                       int64_t* out_count, void* stream);
+
+/* introspection (host values) */
+int pfn_slot_info(pfn_ctx* ctx, int slot, int64_t* N, int32_t* F, int32_t* T, int64_t* kv_bytes);
+/* number of kernels this library launched since creation (bench.py's gpu_launches) */
+int64_t pfn_launch_count(pfn_ctx* ctx);
+/* per-class device time of the launches recorded while "time_kernels" was on (host arrays of 4:
+ * 0 = item attention of test rows, 1 = item attention of context rows, 2 = projection GEMMs, 3 = other):
+ * summed milliseconds, launch counts and algorithmic FLOPs.  Synchronises the device. */
+int pfn_kernel_times(pfn_ctx* ctx, double* ms, int64_t* counts, double* flops, int reset);
+/* debug / parity: copy a slot's derived quantities to caller device buffers (any may be NULL):
+ * stats[3 * 2G] = mean | std | group scale (first G), y_stats[2] = mean, std, borders[num_buckets+1],
+ * kv[L][T][N][64] bf16 (K 0..31 | V 32..63). */
+int pfn_slot_export(pfn_ctx* ctx, int slot, float* stats, float* y_stats, float* borders, void* kv,
+                    void* stream);
+/* debug / parity: final-layer states of the last forward chunk [rows, T, E] fp32 */
+int pfn_debug_last_states(pfn_ctx* ctx, float* out, int64_t max_floats, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NPE_PFN_B200_H */

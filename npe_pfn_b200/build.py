@@ -1,0 +1,54 @@
+"""Builds the C-ABI shared library (`include/npe_pfn_b200.h`) in-tree with nvcc for sm_100a.
+
+The built `.so` lives at `npe_pfn_b200/_lib/libnpe_pfn_b200.so` (git-ignored, shipped to the GPU box by
+`gpurun`).  nvcc cross-compiles without a GPU, so this also runs in the CPU-only build check.
+"""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(_HERE, "csrc")
+LIB_DIR = os.path.join(_HERE, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libnpe_pfn_b200.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-shared", "-Xcompiler", "-fPIC", "-diag-suppress", "128",
+]
+
+
+def _sources():
+    out = []
+    for root, _d, files in os.walk(CSRC):
+        out += [os.path.join(root, f) for f in files if f.endswith((".cu", ".cuh", ".h"))]
+    out.append(os.path.join(_HERE, "..", "include", "npe_pfn_b200.h"))
+    return out
+
+
+def is_stale() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    return any(os.path.getmtime(s) > t for s in _sources())
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    if not force and not is_stale():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(nvcc):
+        raise RuntimeError("nvcc not found: cannot build libnpe_pfn_b200.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    flags = list(NVCC_FLAGS)
+    if os.path.exists(os.path.join(CSRC, "attn_tc.cuh")):
+        flags.append("-DPFN_WITH_ATTN_TC")
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
+    subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force=True, verbose=True))

@@ -1,0 +1,605 @@
+// npe_pfn_b200 engine: C-ABI (include/npe_pfn_b200.h) over the sm_100a kernels.
+//
+// Replaces, behind the reference's five-call estimator protocol, what the third-party
+// `tabpfn` package does for /root/reference/npe_pfn/npe_pfn.py:140 (fit), :143-145 (predict), :146 (sample)
+// and :149-151 (log density):
+//   pfn_prefill         context rows -> encoder statistics + per-layer head-0 K/V cache kept in HBM
+//   pfn_forward_logits  test rows attend to that cache only -> bar-distribution logits
+//   pfn_sample/logprob  the same forward fused with the head; logits stay inside the library
+//   pfn_accept_compact  support check + ordered compaction of accepted draws
+#include "../../include/npe_pfn_b200.h"
+
+#include <cmath>
+#include <cstring>
+#include <mutex>
+#include <vector>
+
+#include "attn_mma.cuh"
+#ifdef PFN_WITH_ATTN_TC
+#include "attn_tc.cuh"
+#endif
+#include "common.cuh"
+#include "gemm_mma.cuh"
+#include "small_kernels.cuh"
+
+namespace pfn {
+std::string& last_error() {
+    static thread_local std::string e;
+    return e;
+}
+}  // namespace pfn
+
+using namespace pfn;
+
+namespace {
+
+struct Slot {
+    bool valid = false;
+    int64_t N = 0;
+    int F = 0, G = 0, T = 0;
+    float* enc = nullptr;      // kEncFloats
+    float* borders = nullptr;  // num_buckets + 1, original units
+    bf16* kv = nullptr;        // [L][T][N][64]
+    size_t kv_cap = 0;         // bytes
+};
+
+struct Offsets {  // element offsets into the weight blob (npe_pfn_b200/weights.py::blob_layout)
+    size_t enc_x_w, enc_y_w, enc_y_b, pos_emb, feat_wqkv, feat_wo, item_wqkv, item_wo, mlp_w1, mlp_w2, dec_w1, dec_b1,
+        dec_w2, dec_b2, borders, total;
+};
+
+}  // namespace
+
+struct pfn_ctx {
+    pfn_model_config cfg;
+    int device = 0;
+    Offsets off;
+    float* wf = nullptr;  // fp32 blob
+    bf16* wb = nullptr;   // bf16 copy of the blob
+    std::vector<Slot> slots;
+    // workspace (token capacity `cap_tok`)
+    int64_t cap_tok = 0;
+    uint8_t* ws = nullptr;
+    float* xf = nullptr;
+    bf16 *xb = nullptr, *qkv = nullptr, *ob = nullptr, *hb = nullptr;
+    // decoder / head workspace
+    int dec_rows = 4096;
+    bf16* dech = nullptr;
+    float* logits = nullptr;
+    // compaction scratch
+    int32_t* cp_counts = nullptr;
+    int64_t* cp_offsets = nullptr;
+    int64_t cp_cap = 0;
+    int64_t launches = 0;
+    int64_t last_rows = 0;
+    int last_T = 0;
+    int attn_impl = 1;  // 0 = mma.sync, 1 = tcgen05
+    // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
+    int time_kernels = 0;
+    struct Timed { cudaEvent_t a, b; int cls; double flops; };
+    std::vector<Timed> timed;
+    std::vector<cudaEvent_t> ev_pool;
+};
+
+enum KernelClass { KC_ATTN_TEST = 0, KC_ATTN_CTX = 1, KC_GEMM = 2, KC_OTHER = 3, KC_COUNT = 4 };
+
+namespace {
+
+Offsets make_offsets(const pfn_model_config& c) {
+    Offsets o{};
+    size_t p = 0;
+    const size_t E = c.emsize, H = c.nhid, B = c.num_buckets, L = c.nlayers;
+    auto take = [&](size_t n) { size_t r = p; p += n; return r; };
+    o.enc_x_w = take(E * 4);
+    o.enc_y_w = take(E * 2);
+    o.enc_y_b = take(E);
+    o.pos_emb = take((size_t)c.max_groups * E);
+    o.feat_wqkv = take(L * 3 * E * E);
+    o.feat_wo = take(L * E * E);
+    o.item_wqkv = take(L * 3 * E * E);
+    o.item_wo = take(L * E * E);
+    o.mlp_w1 = take(L * H * E);
+    o.mlp_w2 = take(L * E * H);
+    o.dec_w1 = take(H * E);
+    o.dec_b1 = take(H);
+    o.dec_w2 = take(B * H);
+    o.dec_b2 = take(B);
+    o.borders = take(B + 1);
+    o.total = p;
+    return o;
+}
+
+#define PFN_LAUNCH_OK(ctx)                                 \
+    do {                                                   \
+        (ctx)->launches++;                                 \
+        PFN_CUDA_OK(cudaGetLastError());                   \
+    } while (0)
+
+int ensure_workspace(pfn_ctx* c, int64_t tokens, cudaStream_t st) {
+    if (tokens <= c->cap_tok) return 0;
+    PFN_CUDA_OK(cudaStreamSynchronize(st));
+    if (c->ws) PFN_CUDA_OK(cudaFree(c->ws));
+    c->ws = nullptr;
+    c->cap_tok = 0;
+    const int64_t cap = tokens + 1024;
+    const size_t per_tok = (size_t)kE * 4 + kE * 2 + 3 * kE * 2 + kE * 2 + kHid * 2;
+    PFN_CUDA_OK(cudaMalloc(&c->ws, per_tok * (size_t)cap + 1024));
+    uint8_t* p = c->ws;
+    c->xf = reinterpret_cast<float*>(p); p += (size_t)cap * kE * 4;
+    c->xb = reinterpret_cast<bf16*>(p);  p += (size_t)cap * kE * 2;
+    c->qkv = reinterpret_cast<bf16*>(p); p += (size_t)cap * 3 * kE * 2;
+    c->ob = reinterpret_cast<bf16*>(p);  p += (size_t)cap * kE * 2;
+    c->hb = reinterpret_cast<bf16*>(p);
+    c->cap_tok = cap;
+    return 0;
+}
+
+int ensure_decoder_ws(pfn_ctx* c) {
+    if (c->dech) return 0;
+    PFN_CUDA_OK(cudaMalloc(&c->dech, (size_t)c->dec_rows * kHid * 2));
+    PFN_CUDA_OK(cudaMalloc(&c->logits, (size_t)c->dec_rows * c->cfg.num_buckets * 4));
+    return 0;
+}
+
+cudaEvent_t take_event(pfn_ctx* c) {
+    if (!c->ev_pool.empty()) { cudaEvent_t e = c->ev_pool.back(); c->ev_pool.pop_back(); return e; }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+struct TimeScope {  // records an event pair around the launches issued inside its lifetime
+    pfn_ctx* c; cudaStream_t st; pfn_ctx::Timed t; bool on;
+    TimeScope(pfn_ctx* c_, cudaStream_t st_, int cls, double flops) : c(c_), st(st_), on(c_->time_kernels != 0) {
+        if (on) { t.a = take_event(c); t.b = take_event(c); t.cls = cls; t.flops = flops; cudaEventRecord(t.a, st); }
+    }
+    ~TimeScope() { if (on) { cudaEventRecord(t.b, st); c->timed.push_back(t); } }
+};
+
+template <int EPI>
+int gemm(pfn_ctx* c, const GemmArgs& a, cudaStream_t st) {
+    TimeScope ts(c, st, KC_GEMM, 2.0 * (double)a.M * a.N * a.K);
+    PFN_CUDA_OK(launch_gemm_mma<EPI>(a, st));
+    c->launches++;
+    return 0;
+}
+
+int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
+    TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
+#ifdef PFN_WITH_ATTN_TC
+    if (c->attn_impl == 1) {
+        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, st));
+    } else
+#endif
+    {
+        PFN_CUDA_OK(launch_attn_mma(a, kHeads, T, st));
+    }
+    c->launches++;
+    return 0;
+}
+
+// rows through the encoder and all layers; final states in c->xf / c->xb.
+// context (y != null): self-attention between items + cache fill; test rows: attend to the slot cache.
+int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* y, int64_t R, cudaStream_t st) {
+    const int T = s.T, G = s.G;
+    const int64_t tok = R * T;
+    const bool ctx_rows = y != nullptr;
+    const int L = c->cfg.nlayers;
+    if (int rc = ensure_workspace(c, tok, st)) return rc;
+    const float* wf = c->wf;
+    const bf16* wb = c->wb;
+    const Offsets& o = c->off;
+
+    encode_kernel<<<(unsigned)ceil_div(R, ENC_ROWS), kE, 0, st>>>(X, ldx, s.F, G, y, R, s.enc, wf + o.enc_x_w,
+                                                                 wf + o.enc_y_w, wf + o.enc_y_b, wf + o.pos_emb, c->xf,
+                                                                 c->xb);
+    PFN_LAUNCH_OK(c);
+
+    const size_t fa_smem = (size_t)FA_WARPS * 2 * T * 33 * sizeof(float);
+    static size_t fa_smem_set = 0;
+    if (fa_smem > 48 * 1024 && fa_smem > fa_smem_set) {
+        PFN_CUDA_OK(cudaFuncSetAttribute(feature_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem));
+        fa_smem_set = fa_smem;
+    }
+
+    for (int l = 0; l < L; ++l) {
+        GemmArgs g{};
+        g.ln_eps = c->cfg.ln_eps;
+        // ---- attention between features -------------------------------------------------------------
+        g.A = c->xb; g.lda = kE; g.W = wb + o.feat_wqkv + (size_t)l * 3 * kE * kE; g.M = tok; g.N = 3 * kE; g.K = kE;
+        g.Cb = c->qkv; g.ldcb = 3 * kE;
+        if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
+        {
+            const unsigned blocks = (unsigned)std::min<int64_t>(R, 148 * 16);
+            feature_attn_kernel<<<blocks, FA_WARPS * 32, fa_smem, st>>>(c->qkv, R, T, c->ob);
+            PFN_LAUNCH_OK(c);
+        }
+        g.A = c->ob; g.W = wb + o.feat_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;
+        g.Cb = c->xb; g.ldcb = kE; g.Cf = c->xf; g.ldcf = kE;
+        if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+
+        // ---- attention between items ------------------------------------------------------------------
+        AttnArgs a{};
+        a.R = R; a.N = s.N;
+        a.O = c->ob; a.o_row = (int64_t)T * kE; a.o_tok = kE;
+        bf16* cache_l = s.kv + (size_t)l * T * s.N * kKvRow;
+        if (ctx_rows) {
+            g.A = c->xb; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.N = 3 * kE; g.K = kE;
+            g.Cb = c->qkv; g.ldcb = 3 * kE; g.Cf = nullptr;
+            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
+            const int64_t total = R * T * 8;
+            kv_cache_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(c->qkv, R, T, cache_l);
+            PFN_LAUNCH_OK(c);
+            a.Q = c->qkv; a.q_row = (int64_t)T * 3 * kE; a.q_tok = 3 * kE;
+            a.K = c->qkv + kE; a.k_tok = 3 * kE; a.k_row = (int64_t)T * 3 * kE; a.k_head = kDh; a.v_off = kE;
+        } else {
+            g.A = c->xb; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.N = kE; g.K = kE;  // Q rows only
+            g.Cb = c->qkv; g.ldcb = kE; g.Cf = nullptr;
+            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
+            a.Q = c->qkv; a.q_row = (int64_t)T * kE; a.q_tok = kE;
+            a.K = cache_l; a.k_tok = s.N * kKvRow; a.k_row = kKvRow; a.k_head = 0; a.v_off = kDh;
+        }
+        if (int rc = item_attention(c, a, T, st)) return rc;
+        g.A = c->ob; g.W = wb + o.item_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;
+        g.Cb = c->xb; g.ldcb = kE; g.Cf = c->xf; g.ldcf = kE;
+        if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+
+        // ---- MLP ------------------------------------------------------------------------------------------
+        g.A = c->xb; g.W = wb + o.mlp_w1 + (size_t)l * kHid * kE; g.N = kHid; g.K = kE;
+        g.Cb = c->hb; g.ldcb = kHid; g.Cf = nullptr; g.bias = nullptr;
+        if (int rc = gemm<EPI_BIAS_GELU_BF16>(c, g, st)) return rc;
+        g.A = c->hb; g.lda = kHid; g.W = wb + o.mlp_w2 + (size_t)l * kE * kHid; g.N = kE; g.K = kHid;
+        g.Cb = c->xb; g.ldcb = kE; g.Cf = c->xf; g.ldcf = kE;
+        if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+    }
+    c->last_rows = R;
+    c->last_T = T;
+    return 0;
+}
+
+// decoder on the y-token of rows [r0, r0+n) of the last forward chunk -> out[n, B] (row stride ld_out)
+int decode_rows(pfn_ctx* c, const Slot& s, int64_t r0, int64_t n, float* out, int64_t ld_out, cudaStream_t st) {
+    const Offsets& o = c->off;
+    GemmArgs g{};
+    g.A = c->xb + (r0 * s.T + (s.T - 1)) * kE; g.lda = (int64_t)s.T * kE;
+    g.W = c->wb + o.dec_w1; g.M = n; g.N = kHid; g.K = kE;
+    g.Cb = c->dech; g.ldcb = kHid; g.bias = c->wf + o.dec_b1;
+    if (int rc = gemm<EPI_BIAS_GELU_BF16>(c, g, st)) return rc;
+    g = GemmArgs{};
+    g.A = c->dech; g.lda = kHid; g.W = c->wb + o.dec_w2; g.M = n; g.N = c->cfg.num_buckets; g.K = kHid;
+    g.Cf = out; g.ldcf = ld_out; g.bias = c->wf + o.dec_b2; g.scale = 1.0f / c->cfg.softmax_temperature;
+    return gemm<EPI_BIAS_SCALE_F32>(c, g, st);
+}
+
+int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
+    const size_t smem = (size_t)HEAD_WARPS * h.B * sizeof(float);
+    static size_t set_s = 0, set_n = 0;
+    if (sample && smem > set_s) {
+        PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set_s = smem;
+    }
+    if (!sample && smem > set_n) {
+        PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        set_n = smem;
+    }
+    const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(h.M, HEAD_WARPS), 148 * 8);
+    if (sample) head_kernel<true><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
+    else head_kernel<false><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
+    PFN_LAUNCH_OK(c);
+    return 0;
+}
+
+int check_slot(pfn_ctx* c, int slot, bool need_valid) {
+    PFN_REQUIRE(c != nullptr, "null context");
+    PFN_REQUIRE(slot >= 0 && slot < (int)c->slots.size(), "slot out of range");
+    if (need_valid) PFN_REQUIRE(c->slots[slot].valid, "slot has not been prefilled (call pfn_prefill first)");
+    return 0;
+}
+
+int chunk_rows_of(const pfn_ctx* c) { return c->cfg.chunk_rows > 0 ? c->cfg.chunk_rows : 16384; }
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+int pfn_abi_version(void) { return PFN_ABI_VERSION; }
+const char* pfn_last_error(void) { return last_error().c_str(); }
+
+int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_floats, int device, void* stream,
+                   pfn_ctx** out) {
+    PFN_REQUIRE(cfg && weights && out, "null argument");
+    PFN_REQUIRE(cfg->emsize == kE && cfg->nhead == kHeads && cfg->nhid == kHid,
+                "this build is specialised for emsize 192, 6 heads, hidden 768");
+    PFN_REQUIRE(cfg->nlayers >= 1 && cfg->num_buckets >= 2 && cfg->num_buckets % 2 == 0, "bad layer/bucket count");
+    PFN_REQUIRE(cfg->max_groups >= 1 && cfg->max_groups * 2 <= kMaxFeat, "max_groups out of range");
+    PFN_REQUIRE(cfg->max_slots >= 1, "max_slots must be >= 1");
+    PFN_REQUIRE(cfg->softmax_temperature > 0.f, "softmax_temperature must be > 0");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    PFN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
+    PFN_REQUIRE(prop.major == 10, "npe_pfn_b200 kernels are built for sm_100a (Blackwell B200) only");
+    pfn_ctx* c = new pfn_ctx();
+    c->cfg = *cfg;
+    c->device = device;
+    c->off = make_offsets(*cfg);
+    if (c->off.total != n_floats) {
+        last_error() = "weight blob has " + std::to_string(n_floats) + " floats, layout needs " + std::to_string(c->off.total);
+        delete c;
+        return 2;
+    }
+    if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
+    PFN_CUDA_OK(cudaMalloc(&c->wf, n_floats * 4));
+    PFN_CUDA_OK(cudaMalloc(&c->wb, n_floats * 2));
+    PFN_CUDA_OK(cudaMemcpyAsync(c->wf, weights, n_floats * 4, cudaMemcpyDeviceToDevice, st));
+    f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)n_floats, 256), 256, 0, st>>>(c->wf, c->wb, (int64_t)n_floats);
+    PFN_LAUNCH_OK(c);
+    c->slots.resize(cfg->max_slots);
+    for (auto& s : c->slots) {
+        PFN_CUDA_OK(cudaMalloc(&s.enc, kEncFloats * 4));
+        PFN_CUDA_OK(cudaMalloc(&s.borders, (size_t)(cfg->num_buckets + 1) * 4));
+    }
+    PFN_CUDA_OK(cudaStreamSynchronize(st));
+    *out = c;
+    return 0;
+}
+
+int pfn_ctx_destroy(pfn_ctx* c) {
+    if (!c) return 0;
+    cudaSetDevice(c->device);
+    cudaDeviceSynchronize();
+    for (auto& s : c->slots) {
+        cudaFree(s.enc);
+        cudaFree(s.borders);
+        cudaFree(s.kv);
+    }
+    cudaFree(c->wf);
+    cudaFree(c->wb);
+    cudaFree(c->ws);
+    cudaFree(c->dech);
+    cudaFree(c->logits);
+    cudaFree(c->cp_counts);
+    cudaFree(c->cp_offsets);
+    delete c;
+    return 0;
+}
+
+int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
+    PFN_REQUIRE(c && key, "null argument");
+    if (!strcmp(key, "attn_impl")) { c->attn_impl = (int)value; return 0; }
+    if (!strcmp(key, "chunk_rows")) { c->cfg.chunk_rows = (int)value; return 0; }
+    if (!strcmp(key, "time_kernels")) { c->time_kernels = (int)value; return 0; }
+    last_error() = std::string("unknown option ") + key;
+    return 2;
+}
+
+int pfn_prefill(pfn_ctx* c, int slot, const float* X, int64_t ldx, const float* y, int64_t N, int F, void* stream) {
+    if (int rc = check_slot(c, slot, false)) return rc;
+    PFN_REQUIRE(X && y, "null data pointer");
+    PFN_REQUIRE(N >= 1, "context needs at least one row");
+    PFN_REQUIRE(F >= 1 && F <= 2 * c->cfg.max_groups, "feature count out of range");
+    PFN_REQUIRE(ldx >= F, "row stride smaller than feature count");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    Slot& s = c->slots[slot];
+    s.valid = false;
+    s.N = N; s.F = F; s.G = (F + 1) / 2; s.T = s.G + 1;
+    const size_t need = (size_t)c->cfg.nlayers * s.T * N * kKvRow * sizeof(bf16);
+    if (need > s.kv_cap) {
+        PFN_CUDA_OK(cudaStreamSynchronize(st));
+        if (s.kv) PFN_CUDA_OK(cudaFree(s.kv));
+        s.kv = nullptr; s.kv_cap = 0;
+        PFN_CUDA_OK(cudaMalloc(&s.kv, need));
+        s.kv_cap = need;
+    }
+    fit_stats_kernel<<<2 * s.G + 1, 256, 0, st>>>(X, ldx, y, N, F, s.G, s.enc);
+    PFN_LAUNCH_OK(c);
+    const int nb1 = c->cfg.num_buckets + 1;
+    fit_finalize_kernel<<<(unsigned)ceil_div(std::max(nb1, s.G), 256), 256, 0, st>>>(s.enc, s.G, c->wf + c->off.borders,
+                                                                                    nb1, s.borders);
+    PFN_LAUNCH_OK(c);
+    if (int rc = forward_rows(c, s, X, ldx, y, N, st)) return rc;
+    s.valid = true;
+    return 0;
+}
+
+int pfn_forward_logits(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_t M, float* out, int64_t ld_out,
+                       void* stream) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    PFN_REQUIRE(M >= 0, "negative row count");
+    if (M == 0) return 0;
+    PFN_REQUIRE(X && out, "null data pointer");
+    Slot& s = c->slots[slot];
+    PFN_REQUIRE(ldx >= s.F, "row stride smaller than the slot's feature count");
+    PFN_REQUIRE(ld_out >= c->cfg.num_buckets && ld_out % 2 == 0, "logits row stride must be even and >= num_buckets");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    if (int rc = ensure_decoder_ws(c)) return rc;
+    const int64_t chunk = chunk_rows_of(c);
+    for (int64_t r0 = 0; r0 < M; r0 += chunk) {
+        const int64_t R = std::min(chunk, M - r0);
+        if (int rc = forward_rows(c, s, X + r0 * ldx, ldx, nullptr, R, st)) return rc;
+        for (int64_t d0 = 0; d0 < R; d0 += c->dec_rows) {
+            const int64_t n = std::min<int64_t>(c->dec_rows, R - d0);
+            if (int rc = decode_rows(c, s, d0, n, out + (r0 + d0) * ld_out, ld_out, st)) return rc;
+        }
+    }
+    return 0;
+}
+
+int pfn_head_sample(pfn_ctx* c, int slot, const float* logits, int64_t ld_logits, int64_t M, const float* uniforms,
+                    uint64_t seed, uint64_t row0, uint64_t offset, float* out_theta, int64_t ld_theta, int32_t* out_bin,
+                    float* out_u, float* out_logp, float eps, int accumulate, void* stream) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    if (M == 0) return 0;
+    PFN_REQUIRE(logits && out_theta, "null data pointer");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    HeadArgs h{};
+    h.logits = logits; h.ld_logits = ld_logits; h.M = M; h.B = c->cfg.num_buckets; h.borders = c->slots[slot].borders;
+    h.uniforms = uniforms; h.seed = seed; h.row0 = row0; h.offset = offset;
+    h.out_theta = out_theta; h.ld_theta = ld_theta; h.out_bin = out_bin; h.out_u = out_u; h.out_logp = out_logp;
+    h.log_eps = std::log((float)eps); h.accumulate = accumulate;
+    return launch_head(c, h, true, (cudaStream_t)stream);
+}
+
+int pfn_head_nll(pfn_ctx* c, int slot, const float* logits, int64_t ld_logits, int64_t M, const float* y, int64_t ld_y,
+                 float* out_nll, float* out_logp, float eps, int accumulate, void* stream) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    if (M == 0) return 0;
+    PFN_REQUIRE(logits && y, "null data pointer");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    HeadArgs h{};
+    h.logits = logits; h.ld_logits = ld_logits; h.M = M; h.B = c->cfg.num_buckets; h.borders = c->slots[slot].borders;
+    h.y = y; h.ld_y = ld_y; h.out_nll = out_nll; h.out_logp = out_logp;
+    h.log_eps = std::log((float)eps); h.accumulate = accumulate;
+    return launch_head(c, h, false, (cudaStream_t)stream);
+}
+
+static int fused_step(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_t M, bool sample, const float* uniforms,
+                      uint64_t seed, uint64_t row0, uint64_t offset, float* out_theta, int64_t ld_theta,
+                      int32_t* out_bin, const float* y, int64_t ld_y, float* out_logp, float eps, int accumulate,
+                      void* stream) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    PFN_REQUIRE(M >= 0, "negative row count");
+    if (M == 0) return 0;
+    PFN_REQUIRE(X, "null data pointer");
+    Slot& s = c->slots[slot];
+    PFN_REQUIRE(ldx >= s.F, "row stride smaller than the slot's feature count");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    if (int rc = ensure_decoder_ws(c)) return rc;
+    const int64_t chunk = chunk_rows_of(c);
+    const int B = c->cfg.num_buckets;
+    for (int64_t r0 = 0; r0 < M; r0 += chunk) {
+        const int64_t R = std::min(chunk, M - r0);
+        if (int rc = forward_rows(c, s, X + r0 * ldx, ldx, nullptr, R, st)) return rc;
+        for (int64_t d0 = 0; d0 < R; d0 += c->dec_rows) {
+            const int64_t n = std::min<int64_t>(c->dec_rows, R - d0);
+            if (int rc = decode_rows(c, s, d0, n, c->logits, B, st)) return rc;
+            const int64_t g0 = r0 + d0;
+            HeadArgs h{};
+            h.logits = c->logits; h.ld_logits = B; h.M = n; h.B = B; h.borders = s.borders;
+            h.log_eps = std::log((float)eps); h.accumulate = accumulate;
+            h.out_logp = out_logp ? out_logp + g0 : nullptr;
+            if (sample) {
+                h.uniforms = uniforms ? uniforms + g0 : nullptr;
+                h.seed = seed; h.row0 = row0 + (uint64_t)g0; h.offset = offset;
+                h.out_theta = out_theta + g0 * ld_theta; h.ld_theta = ld_theta;
+                h.out_bin = out_bin ? out_bin + g0 : nullptr;
+            } else {
+                h.y = y + g0 * ld_y; h.ld_y = ld_y;
+            }
+            if (int rc = launch_head(c, h, sample, st)) return rc;
+        }
+    }
+    return 0;
+}
+
+int pfn_sample(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_t M, const float* uniforms, uint64_t seed,
+               uint64_t row0, uint64_t offset, float* out_theta, int64_t ld_theta, int32_t* out_bin, float* out_logp,
+               float eps, int accumulate, void* stream) {
+    PFN_REQUIRE(out_theta || M == 0, "null output pointer");
+    return fused_step(c, slot, X, ldx, M, true, uniforms, seed, row0, offset, out_theta, ld_theta, out_bin, nullptr, 0,
+                      out_logp, eps, accumulate, stream);
+}
+
+int pfn_logprob(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_t M, const float* y, int64_t ld_y,
+                float* out_logp, float eps, int accumulate, void* stream) {
+    PFN_REQUIRE((y && out_logp) || M == 0, "null data pointer");
+    return fused_step(c, slot, X, ldx, M, false, nullptr, 0, 0, 0, nullptr, 0, nullptr, y, ld_y, out_logp, eps,
+                      accumulate, stream);
+}
+
+int pfn_accept_compact(pfn_ctx* c, const float* theta, int64_t ld, int64_t M, int dim, const float* lo, const float* hi,
+                       const uint8_t* mask, int64_t* out_idx, float* out_rows, int64_t* out_count, void* stream) {
+    PFN_REQUIRE(c && out_count, "null argument");
+    PFN_REQUIRE(M >= 0 && dim >= 1 && ld >= dim, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    if (M == 0) {
+        PFN_CUDA_OK(cudaMemsetAsync(out_count, 0, sizeof(int64_t), st));
+        return 0;
+    }
+    PFN_REQUIRE(theta, "null data pointer");
+    const int64_t nblocks = ceil_div(M, CP_THREADS);
+    if (nblocks > c->cp_cap) {
+        PFN_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(c->cp_counts);
+        cudaFree(c->cp_offsets);
+        c->cp_cap = 0;
+        PFN_CUDA_OK(cudaMalloc(&c->cp_counts, (size_t)(nblocks + 1024) * 4));
+        PFN_CUDA_OK(cudaMalloc(&c->cp_offsets, (size_t)(nblocks + 1024) * 8));
+        c->cp_cap = nblocks + 1024;
+    }
+    compact_count_kernel<<<(unsigned)nblocks, CP_THREADS, 0, st>>>(theta, ld, M, dim, lo, hi, mask, c->cp_counts);
+    PFN_LAUNCH_OK(c);
+    compact_scan_kernel<<<1, 1024, 0, st>>>(c->cp_counts, nblocks, c->cp_offsets, out_count);
+    PFN_LAUNCH_OK(c);
+    if (out_idx || out_rows) {
+        compact_scatter_kernel<<<(unsigned)nblocks, CP_THREADS, 0, st>>>(theta, ld, M, dim, lo, hi, mask, c->cp_offsets,
+                                                                       out_idx, out_rows);
+        PFN_LAUNCH_OK(c);
+    }
+    return 0;
+}
+
+int pfn_slot_info(pfn_ctx* c, int slot, int64_t* N, int32_t* F, int32_t* T, int64_t* kv_bytes) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    const Slot& s = c->slots[slot];
+    if (N) *N = s.N;
+    if (F) *F = s.F;
+    if (T) *T = s.T;
+    if (kv_bytes) *kv_bytes = (int64_t)c->cfg.nlayers * s.T * s.N * kKvRow * (int64_t)sizeof(bf16);
+    return 0;
+}
+
+int64_t pfn_launch_count(pfn_ctx* c) { return c ? c->launches : 0; }
+
+int pfn_kernel_times(pfn_ctx* c, double* ms, int64_t* counts, double* flops, int reset) {
+    PFN_REQUIRE(c && ms && counts && flops, "null argument");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    PFN_CUDA_OK(cudaDeviceSynchronize());
+    for (int k = 0; k < KC_COUNT; ++k) { ms[k] = 0.0; counts[k] = 0; flops[k] = 0.0; }
+    for (auto& t : c->timed) {
+        float e = 0.f;
+        PFN_CUDA_OK(cudaEventElapsedTime(&e, t.a, t.b));
+        ms[t.cls] += e; counts[t.cls] += 1; flops[t.cls] += t.flops;
+    }
+    if (reset) {
+        for (auto& t : c->timed) { c->ev_pool.push_back(t.a); c->ev_pool.push_back(t.b); }
+        c->timed.clear();
+    }
+    return 0;
+}
+
+int pfn_slot_export(pfn_ctx* c, int slot, float* stats, float* y_stats, float* borders, void* kv, void* stream) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    const Slot& s = c->slots[slot];
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    const int Fp = 2 * s.G;
+    if (stats) {
+        PFN_CUDA_OK(cudaMemcpyAsync(stats, s.enc + kEncMean, Fp * 4, cudaMemcpyDeviceToDevice, st));
+        PFN_CUDA_OK(cudaMemcpyAsync(stats + Fp, s.enc + kEncStd, Fp * 4, cudaMemcpyDeviceToDevice, st));
+        PFN_CUDA_OK(cudaMemcpyAsync(stats + 2 * Fp, s.enc + kEncScale, s.G * 4, cudaMemcpyDeviceToDevice, st));
+    }
+    if (y_stats) PFN_CUDA_OK(cudaMemcpyAsync(y_stats, s.enc + kEncY, 3 * 4, cudaMemcpyDeviceToDevice, st));
+    if (borders)
+        PFN_CUDA_OK(cudaMemcpyAsync(borders, s.borders, (size_t)(c->cfg.num_buckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    if (kv) {
+        const size_t bytes = (size_t)c->cfg.nlayers * s.T * s.N * kKvRow * sizeof(bf16);
+        PFN_CUDA_OK(cudaMemcpyAsync(kv, s.kv, bytes, cudaMemcpyDeviceToDevice, st));
+    }
+    return 0;
+}
+
+int pfn_debug_last_states(pfn_ctx* c, float* out, int64_t max_floats, void* stream) {
+    PFN_REQUIRE(c && out, "null argument");
+    const int64_t n = c->last_rows * c->last_T * kE;
+    PFN_REQUIRE(n > 0 && n <= max_floats, "no forward has run or output buffer too small");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    PFN_CUDA_OK(cudaMemcpyAsync(out, c->xf, (size_t)n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+}  // extern "C"

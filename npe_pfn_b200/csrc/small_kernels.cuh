@@ -1,0 +1,521 @@
+// HBM-bound kernels around the transformer: context statistics (fit), the per-cell feature encoder,
+// attention between features (tiny T), the head-0 K/V cache writer, the bar-distribution head
+// (softmax -> integer CDF -> inverse-CDF sample / log density) and support check + ordered compaction.
+//
+// The head follows the arithmetic spec of oracle/bar_head.c exactly (deterministic exp, 2^40 fixed
+// point probabilities, integer prefix sums) so bucket indices and samples are bit-identical to the
+// oracle for identical logits and uniforms.
+#pragma once
+#include "common.cuh"
+
+namespace pfn {
+
+constexpr int kMaxFeat = 128;  // 2 * max_groups
+constexpr int kEncFloats = 2 * kMaxFeat + kMaxFeat / 2 + 4;
+// slot "enc" buffer layout (floats): mean[128] | std[128] | scale[64] | y_mean, y_std, y_fill, pad
+constexpr int kEncMean = 0, kEncStd = kMaxFeat, kEncScale = 2 * kMaxFeat, kEncY = 2 * kMaxFeat + kMaxFeat / 2;
+
+// ---------------------------------------------------------------------------------------------
+// fit statistics (oracle/tabpfn_oracle.py::EncoderStats,
+// oracle/estimator.py::y_standardise).  One block per padded feature column + one for y.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double block_sum_double(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < nw; ++w) t += sh[w];  // fixed order: deterministic
+    return t;
+}
+
+__global__ void __launch_bounds__(256) fit_stats_kernel(const float* __restrict__ X, int64_t ldx,
+                                                        const float* __restrict__ y, int64_t N, int F, int G,
+                                                        float* __restrict__ enc) {
+    __shared__ double sh[8];
+    const int c = blockIdx.x;
+    const int Fp = 2 * G;
+    if (c < Fp) {
+        if (c >= F) {  // zero padding column: constant by construction
+            if (threadIdx.x == 0) { enc[kEncMean + c] = 0.f; enc[kEncStd + c] = 0.f; }
+            return;
+        }
+        double s = 0.0, cnt = 0.0;
+        for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+            float v = X[i * ldx + c];
+            if (isfinite(v)) { s += (double)v; cnt += 1.0; }
+        }
+        s = block_sum_double(s, sh);
+        cnt = block_sum_double(cnt, sh);
+        const double mean = s / fmax(cnt, 1.0);
+        double q = 0.0;
+        for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+            float v = X[i * ldx + c];
+            double d = isfinite(v) ? (double)v - mean : 0.0;
+            q += d * d;
+        }
+        q = block_sum_double(q, sh);
+        if (threadIdx.x == 0) {
+            double var = N > 1 ? q / (double)(N - 1) : 0.0;
+            enc[kEncMean + c] = (float)mean;
+            enc[kEncStd + c] = (float)sqrt(var);
+        }
+        return;
+    }
+    // y column
+    double s = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) s += (double)y[i];
+    s = block_sum_double(s, sh);
+    const double mean = s / (double)N;
+    double q = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) {
+        double d = (double)y[i] - mean;
+        q += d * d;
+    }
+    q = block_sum_double(q, sh);
+    const double std_d = N > 1 ? sqrt(q / (double)(N - 1)) : 0.0;
+    const float mean32 = (float)mean;
+    float std32 = (float)std_d;
+    if (!isfinite(std32) || std32 == 0.f) std32 = 1.f;
+    double z = 0.0;
+    for (int64_t i = threadIdx.x; i < N; i += blockDim.x) z += (double)((y[i] - mean32) / std32);
+    z = block_sum_double(z, sh);
+    if (threadIdx.x == 0) {
+        enc[kEncY + 0] = mean32;
+        enc[kEncY + 1] = std32;
+        enc[kEncY + 2] = (float)(z / (double)N);
+        enc[kEncY + 3] = 0.f;
+    }
+}
+
+// group scale sqrt(2 / #non-constant features) and the bucket borders in original units
+__global__ void fit_finalize_kernel(float* __restrict__ enc, int G, const float* __restrict__ borders, int nb1,
+                                    float* __restrict__ borders_out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < G) {
+        int used = (enc[kEncStd + 2 * i] != 0.f) + (enc[kEncStd + 2 * i + 1] != 0.f);
+        enc[kEncScale + i] = sqrtf(2.0f / (float)max(used, 1));
+    }
+    if (i < nb1) borders_out[i] = fmaf(borders[i], enc[kEncY + 1], enc[kEncY + 0]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// cell encoder: rows x F raw features (+ y for context rows) -> token grid [R, T, E] (fp32 + bf16)
+// (oracle/tabpfn_oracle.py::encode_x / encode_y_ctx / encode_y_test)
+// ---------------------------------------------------------------------------------------------
+constexpr int ENC_ROWS = 4;
+__global__ void __launch_bounds__(kE) encode_kernel(const float* __restrict__ X, int64_t ldx, int F, int G,
+                                                    const float* __restrict__ y /* null: test rows */,
+                                                    int64_t R, const float* __restrict__ enc,
+                                                    const float* __restrict__ enc_x_w, const float* __restrict__ enc_y_w,
+                                                    const float* __restrict__ enc_y_b, const float* __restrict__ pos_emb,
+                                                    float* __restrict__ xf, bf16* __restrict__ xb) {
+    const int e = threadIdx.x;
+    const int T = G + 1;
+    const float4 wx = *reinterpret_cast<const float4*>(enc_x_w + 4 * e);
+    const float2 wy = *reinterpret_cast<const float2*>(enc_y_w + 2 * e);
+    const float by = enc_y_b[e];
+    const float y_mean = enc[kEncY + 0], y_std = enc[kEncY + 1], y_fill = enc[kEncY + 2];
+    for (int rr = 0; rr < ENC_ROWS; ++rr) {
+        const int64_t r = (int64_t)blockIdx.x * ENC_ROWS + rr;
+        if (r >= R) return;
+        const float* xr = X + r * ldx;
+        float* of = xf + r * T * kE;
+        bf16* ob = xb + r * T * kE;
+        for (int g = 0; g < G; ++g) {
+            float f[2], ind[2];
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+                const int c = 2 * g + j;
+                float v = c < F ? xr[c] : 0.f;
+                float id = 0.f;
+                if (isnan(v)) id = -2.f;
+                else if (isinf(v)) id = v > 0.f ? 2.f : 4.f;
+                const float mean = enc[kEncMean + c], sd = enc[kEncStd + c];
+                const float filled = isfinite(v) ? v : mean;
+                float xn = (filled - mean) / (sd + 1e-16f);
+                if (sd == 0.f) xn = 0.f;
+                xn = fminf(fmaxf(xn, -100.f), 100.f);
+                f[j] = xn * enc[kEncScale + g];
+                ind[j] = id;
+            }
+            float v = f[0] * wx.x;
+            v = fmaf(f[1], wx.y, v);
+            v = fmaf(ind[0], wx.z, v);
+            v = fmaf(ind[1], wx.w, v);
+            v += pos_emb[g * kE + e];
+            of[g * kE + e] = v;
+            ob[g * kE + e] = __float2bfloat16_rn(v);
+        }
+        float y0, y1;
+        if (y) { y0 = (y[r] - y_mean) / y_std; y1 = 0.f; }
+        else   { y0 = y_fill; y1 = -2.f; }
+        float v = fmaf(y1, wy.y, y0 * wy.x) + by;
+        of[G * kE + e] = v;
+        ob[G * kE + e] = __float2bfloat16_rn(v);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// attention between features: for every row, MHA over its T tokens (T = G+1 is tiny).
+// One warp per (row, head); fp32 math on bf16 q/k/v.  qkv [R*T, 576] = q | k | v, head h at h*32.
+// ---------------------------------------------------------------------------------------------
+constexpr int FA_WARPS = 6;
+__global__ void __launch_bounds__(FA_WARPS * 32) feature_attn_kernel(const bf16* __restrict__ qkv, int64_t R, int T,
+                                                                     bf16* __restrict__ out) {
+    extern __shared__ float fa_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float* sK = fa_smem + (size_t)warp * 2 * T * 33;
+    float* sV = sK + T * 33;
+    const float scale_log2 = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+    const int nj = (T + 31) >> 5;                                          // key groups of 32 (<= 3)
+    for (int64_t r = blockIdx.x; r < R; r += gridDim.x) {
+        const int h = warp;
+        const bf16* base = qkv + r * T * 3 * kE + h * kDh;
+        __syncwarp();
+        for (int j = 0; j < T; ++j) {
+            sK[j * 33 + lane] = __bfloat162float(base[(int64_t)j * 3 * kE + kE + lane]);
+            sV[j * 33 + lane] = __bfloat162float(base[(int64_t)j * 3 * kE + 2 * kE + lane]);
+        }
+        __syncwarp();
+        for (int i = 0; i < T; ++i) {
+            const float qd = __bfloat162float(base[(int64_t)i * 3 * kE + lane]);
+            float s[3] = {0.f, 0.f, 0.f};
+#pragma unroll 8
+            for (int d = 0; d < kDh; ++d) {
+                const float q = __shfl_sync(0xffffffffu, qd, d);
+#pragma unroll
+                for (int jj = 0; jj < 3; ++jj) {
+                    const int j = jj * 32 + lane;
+                    if (jj < nj && j < T) s[jj] = fmaf(q, sK[j * 33 + d], s[jj]);
+                }
+            }
+            float m = -INFINITY;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                const int j = jj * 32 + lane;
+                s[jj] = (jj < nj && j < T) ? s[jj] * scale_log2 : -INFINITY;
+                m = fmaxf(m, s[jj]);
+            }
+            m = warp_max(m);
+            float p[3], l = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) { p[jj] = exp2f(s[jj] - m); l += p[jj]; }
+            l = warp_sum(l);
+            float o = 0.f;
+#pragma unroll
+            for (int jj = 0; jj < 3; ++jj) {
+                if (jj < nj) {
+                    const int jmax = min(32, T - jj * 32);
+                    for (int j = 0; j < jmax; ++j) {
+                        const float pj = __shfl_sync(0xffffffffu, p[jj], j);
+                        o = fmaf(pj, sV[(jj * 32 + j) * 33 + lane], o);
+                    }
+                }
+            }
+            out[(r * T + i) * kE + h * kDh + lane] = __float2bfloat16_rn(o / l);
+        }
+    }
+}
+
+// head-0 K/V of the context rows -> cache [T][N][64] (K 0..31 | V 32..63) for one layer
+__global__ void kv_cache_kernel(const bf16* __restrict__ qkv, int64_t N, int T, bf16* __restrict__ cache) {
+    // one thread per 16 bytes: (n, t, part in 0..7): parts 0-3 = K, 4-7 = V
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t total = N * T * 8;
+    if (idx >= total) return;
+    const int part = (int)(idx & 7);
+    const int64_t nt = idx >> 3;
+    const int t = (int)(nt % T);
+    const int64_t n = nt / T;
+    const bf16* src = qkv + (n * T + t) * 3 * kE + (part < 4 ? kE + part * 8 : 2 * kE + (part - 4) * 8);
+    bf16* dst = cache + ((int64_t)t * N + n) * kKvRow + part * 8;
+    *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+}
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restrict__ out, int64_t n) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = __float2bfloat16_rn(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// bar-distribution head (oracle/bar_head.c is the arithmetic spec)
+// ---------------------------------------------------------------------------------------------
+constexpr int kQShift = 40;
+
+__device__ __forceinline__ float exp_det(float t) {
+    if (!(t > -64.0f)) t = -64.0f;
+    const float x = __fmul_rn(t, 0x1.715476p+0f);
+    const float n = floorf(x);
+    const float f = __fsub_rn(x, n);
+    float p = 0x1.ca8f0ap-13f;
+    p = __fmaf_rn(p, f, 0x1.44d4d2p-10f);
+    p = __fmaf_rn(p, f, 0x1.3d54d8p-7f);
+    p = __fmaf_rn(p, f, 0x1.c67f50p-5f);
+    p = __fmaf_rn(p, f, 0x1.ebfdf2p-3f);
+    p = __fmaf_rn(p, f, 0x1.62e428p-1f);
+    p = __fmaf_rn(p, f, 0x1.000000p+0f);
+    const float s = __uint_as_float((uint32_t)((int)n + 127) << 23);
+    return __fmul_rn(p, s);
+}
+
+__device__ __forceinline__ unsigned long long quantize_q40(float e) {
+    const uint32_t b = __float_as_uint(e);
+    const int ex = (int)((b >> 23) & 0xff);
+    if (ex == 0) return 0ull;
+    const unsigned long long m = (unsigned long long)((b & 0x7fffffu) | 0x800000u);
+    const int sh = ex - 127 - 23 + kQShift;
+    if (sh >= 0) return m << sh;
+    if (sh <= -64) return 0ull;
+    return m >> (-sh);
+}
+
+__device__ __forceinline__ void philox4x32_10(uint64_t seed, uint64_t row, uint64_t offset, uint32_t (&c)[4]) {
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+    c[0] = (uint32_t)row; c[1] = (uint32_t)(row >> 32); c[2] = (uint32_t)offset; c[3] = (uint32_t)(offset >> 32);
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n2 = hi0 ^ c[3] ^ k1;
+        c[0] = n0; c[1] = lo1; c[2] = n2; c[3] = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+}
+
+__device__ __forceinline__ unsigned long long warp_sum_u64(unsigned long long v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// first k in [0, B] with borders[k] >= y, minus one, clamped to [0, B-1]
+__device__ __forceinline__ int bucket_of(const float* __restrict__ borders, int B, float y) {
+    int lo = 0, hi = B + 1;
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (borders[mid] < y) lo = mid + 1; else hi = mid;
+    }
+    return min(max(lo - 1, 0), B - 1);
+}
+
+__device__ __forceinline__ double halfnormal_logpdf(double v, double scale) {
+    return log(2.0) - log(scale) - 0.5 * log(2.0 * 3.14159265358979323846) - 0.5 * (v / scale) * (v / scale);
+}
+
+// log density of y under the bar distribution given the row's max logit m and log partition
+__device__ double bar_logp(const float* __restrict__ lg, int B, const float* __restrict__ borders, float m,
+                           double logZ, float y) {
+    const int idx = bucket_of(borders, B, y);
+    const double width = (double)borders[idx + 1] - (double)borders[idx];
+    double logp = ((double)lg[idx] - (double)m) - logZ - log(width);
+    const double kIcdfHalf = 0.6744897501960817;
+    if (idx == 0) {
+        const double w0 = (double)borders[1] - (double)borders[0];
+        double v = (double)borders[1] - (double)y;
+        if (v < 1e-8) v = 1e-8;
+        logp += halfnormal_logpdf(v, w0 / kIcdfHalf) + log(w0);
+    } else if (idx == B - 1) {
+        const double wl = (double)borders[B] - (double)borders[B - 1];
+        double v = (double)y - (double)borders[B - 1];
+        if (v < 1e-8) v = 1e-8;
+        logp += halfnormal_logpdf(v, wl / kIcdfHalf) + log(wl);
+    }
+    return logp;
+}
+
+struct HeadArgs {
+    const float* logits;
+    int64_t ld_logits;  // 0 = every row reads the same logits row
+    int64_t M;
+    int B;
+    const float* borders;  // [B+1], original units
+    const float* uniforms;
+    uint64_t seed, row0, offset;
+    float* out_theta;
+    int64_t ld_theta;
+    int32_t* out_bin;
+    float* out_u;
+    float* out_logp;
+    float log_eps;
+    int accumulate;
+    const float* y;  // nll mode
+    int64_t ld_y;
+    float* out_nll;
+};
+
+constexpr int HEAD_WARPS = 4;
+
+// one warp per row: stage the row in shared memory, max, integer partition sum, inverse CDF
+template <bool SAMPLE>
+__global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(HeadArgs a) {
+    extern __shared__ float head_smem[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B = a.B;
+    float* row = head_smem + (size_t)warp * B;
+    const double kLn2x40 = 40.0 * 0.6931471805599453;
+    for (int64_t r = (int64_t)blockIdx.x * HEAD_WARPS + warp; r < a.M; r += (int64_t)gridDim.x * HEAD_WARPS) {
+        const float* lg = a.logits + r * a.ld_logits;
+        __syncwarp();
+        float m = -INFINITY;
+        for (int i = lane; i < B; i += 32) {
+            const float v = lg[i];
+            row[i] = v;
+            m = fmaxf(m, v);
+        }
+        m = warp_max(m);
+        __syncwarp();
+        unsigned long long z = 0ull;
+        for (int i = lane; i < B; i += 32) z += quantize_q40(exp_det(row[i] - m));
+        const unsigned long long Z = warp_sum_u64(z);
+        const double logZ = log((double)Z) - kLn2x40;
+
+        if (!SAMPLE) {
+            if (lane == 0) {
+                const float yv = a.y[r * a.ld_y];
+                const double logp = bar_logp(row, B, a.borders, m, logZ, yv);
+                if (a.out_nll) a.out_nll[r] = (float)(-logp);
+                if (a.out_logp) {
+                    float lp = (float)logp;
+                    if (lp == -INFINITY) lp = a.log_eps;
+                    a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+                }
+            }
+            continue;
+        }
+
+        float u;
+        if (a.uniforms) u = a.uniforms[r];
+        else {
+            uint32_t c[4];
+            philox4x32_10(a.seed, a.row0 + (uint64_t)r, a.offset, c);
+            u = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;  // strictly inside (0, 1)
+        }
+        const double target = (double)u * (double)Z;
+        unsigned long long run = 0ull;  // sum of all buckets before this chunk
+        int idx = -1;
+        unsigned long long Cprev = 0ull, qsel = 0ull;
+        for (int base = 0; base < B && idx < 0; base += 32) {
+            const int i = base + lane;
+            const unsigned long long q = i < B ? quantize_q40(exp_det(row[i] - m)) : 0ull;
+            unsigned long long c = q;  // inclusive scan over lanes
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long t = __shfl_up_sync(0xffffffffu, c, o);
+                if (lane >= o) c += t;
+            }
+            c += run;
+            const bool below = (i < B) && ((double)c < target);
+            const unsigned bal = __ballot_sync(0xffffffffu, below);
+            const int nbelow = __popc(bal);
+            const int nvalid = min(32, B - base);
+            if (nbelow < nvalid) {  // the first lane that is not below holds the bucket
+                idx = base + nbelow;
+                const unsigned long long csel = __shfl_sync(0xffffffffu, c, nbelow);
+                qsel = __shfl_sync(0xffffffffu, q, nbelow);
+                Cprev = csel - qsel;
+            }
+            run = __shfl_sync(0xffffffffu, c, 31);
+        }
+        if (idx < 0) { idx = B - 1; Cprev = Z; qsel = 0ull; }
+        if (lane == 0) {
+            double frac = qsel ? (target - (double)Cprev) / (double)qsel : 0.0;
+            frac = fmin(fmax(frac, 0.0), 1.0);
+            const double lo = (double)a.borders[idx], hi = (double)a.borders[idx + 1];
+            const float th = (float)(lo + (hi - lo) * frac);
+            a.out_theta[r * a.ld_theta] = th;
+            if (a.out_bin) a.out_bin[r] = idx;
+            if (a.out_u) a.out_u[r] = u;
+            if (a.out_logp) {
+                float lp = (float)bar_logp(row, B, a.borders, m, logZ, th);
+                if (lp == -INFINITY) lp = a.log_eps;
+                a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// support check + ordered stream compaction (accept_reject_sampler.py:54-62)
+// ---------------------------------------------------------------------------------------------
+constexpr int CP_THREADS = 256;
+
+__device__ __forceinline__ bool row_accepted(const float* __restrict__ theta, int64_t ld, int64_t r, int dim,
+                                             const float* __restrict__ lo, const float* __restrict__ hi,
+                                             const uint8_t* __restrict__ mask) {
+    bool ok = mask ? mask[r] != 0 : true;
+    for (int j = 0; j < dim; ++j) {
+        const float v = theta[r * ld + j];
+        ok = ok && isfinite(v);
+        if (lo) ok = ok && (v >= lo[j]);
+        if (hi) ok = ok && (v <= hi[j]);
+    }
+    return ok;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const float* theta, int64_t ld, int64_t M, int dim,
+                                                                   const float* lo, const float* hi,
+                                                                   const uint8_t* mask, int32_t* block_counts) {
+    __shared__ int wc[CP_THREADS / 32];
+    const int64_t r = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x;
+    const bool ok = r < M && row_accepted(theta, ld, r, dim, lo, hi, mask);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int s = 0;
+        for (int w = 0; w < CP_THREADS / 32; ++w) s += wc[w];
+        block_counts[blockIdx.x] = s;
+    }
+}
+
+// exclusive scan of the block counts (single block; nblocks <= a few 10^4)
+__global__ void __launch_bounds__(1024) compact_scan_kernel(const int32_t* block_counts, int64_t nblocks,
+                                                            int64_t* block_offsets, int64_t* out_count) {
+    __shared__ long long sh[1024];
+    __shared__ long long carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int64_t base = 0; base < nblocks; base += 1024) {
+        const int64_t i = base + threadIdx.x;
+        const long long v = i < nblocks ? block_counts[i] : 0;
+        sh[threadIdx.x] = v;
+        __syncthreads();
+        for (int o = 1; o < 1024; o <<= 1) {
+            long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
+            __syncthreads();
+            sh[threadIdx.x] += t;
+            __syncthreads();
+        }
+        if (i < nblocks) block_offsets[i] = carry + sh[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 0) carry += sh[1023];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out_count = carry;
+}
+
+__global__ void __launch_bounds__(CP_THREADS) compact_scatter_kernel(const float* theta, int64_t ld, int64_t M, int dim,
+                                                                     const float* lo, const float* hi,
+                                                                     const uint8_t* mask, const int64_t* block_offsets,
+                                                                     int64_t* out_idx, float* out_rows) {
+    __shared__ int wc[CP_THREADS / 32];
+    const int64_t r = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x;
+    const bool ok = r < M && row_accepted(theta, ld, r, dim, lo, hi, mask);
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) wc[warp] = __popc(bal);
+    __syncthreads();
+    int before = 0;
+    for (int w = 0; w < warp; ++w) before += wc[w];
+    if (ok) {
+        const int64_t pos = block_offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));
+        if (out_idx) out_idx[pos] = r;
+        if (out_rows)
+            for (int j = 0; j < dim; ++j) out_rows[pos * dim + j] = theta[r * ld + j];
+    }
+}
+
+}  // namespace pfn

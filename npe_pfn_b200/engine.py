@@ -1,0 +1,293 @@
+"""ctypes binding of the C-ABI in `include/npe_pfn_b200.h` (thin: pointers + sizes only).
+
+`Engine` owns one `pfn_ctx` on one CUDA device.  Torch is used here only for device memory and the
+current stream; every compute call goes through `libnpe_pfn_b200.so`.  There is no CPU fallback: if the
+library is missing, cannot be built, or no sm_100 device is visible, construction raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+from . import build as _build
+from .weights import PFNConfig, PFNWeights
+
+c = ctypes
+
+
+class pfn_model_config(ctypes.Structure):
+    _fields_ = [
+        ("emsize", c.c_int32), ("nhead", c.c_int32), ("nlayers", c.c_int32), ("nhid", c.c_int32),
+        ("num_buckets", c.c_int32), ("max_groups", c.c_int32), ("max_slots", c.c_int32), ("chunk_rows", c.c_int32),
+        ("ln_eps", c.c_float), ("softmax_temperature", c.c_float),
+    ]
+
+
+#: every symbol `include/npe_pfn_b200.h` declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "pfn_abi_version", "pfn_last_error", "pfn_ctx_create", "pfn_ctx_destroy", "pfn_set_option", "pfn_prefill",
+    "pfn_forward_logits", "pfn_head_sample", "pfn_head_nll", "pfn_sample", "pfn_logprob", "pfn_accept_compact",
+    "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_debug_last_states",
+]
+
+_LIB = None
+
+
+def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
+    """Load (building if stale and nvcc is available) the in-tree shared library."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = _build.LIB_PATH
+    if build_if_missing and _build.is_stale():
+        try:
+            _build.build_library()
+        except Exception as e:  # stale-but-present library is still usable; missing one is fatal
+            if not os.path.exists(path):
+                raise RuntimeError(f"libnpe_pfn_b200.so is missing and could not be built: {e}") from e
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'`")
+    L = ctypes.CDLL(path)
+    vp, i64, u64, i32, f32 = c.c_void_p, c.c_int64, c.c_uint64, c.c_int32, c.c_float
+    L.pfn_abi_version.restype = c.c_int
+    L.pfn_last_error.restype = c.c_char_p
+    L.pfn_ctx_create.restype = c.c_int
+    L.pfn_ctx_create.argtypes = [c.POINTER(pfn_model_config), vp, c.c_size_t, c.c_int, vp, c.POINTER(vp)]
+    L.pfn_ctx_destroy.restype = c.c_int
+    L.pfn_ctx_destroy.argtypes = [vp]
+    L.pfn_set_option.restype = c.c_int
+    L.pfn_set_option.argtypes = [vp, c.c_char_p, i64]
+    L.pfn_prefill.restype = c.c_int
+    L.pfn_prefill.argtypes = [vp, c.c_int, vp, i64, vp, i64, c.c_int, vp]
+    L.pfn_forward_logits.restype = c.c_int
+    L.pfn_forward_logits.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp]
+    L.pfn_head_sample.restype = c.c_int
+    L.pfn_head_sample.argtypes = [vp, c.c_int, vp, i64, i64, vp, u64, u64, u64, vp, i64, vp, vp, vp, f32, c.c_int, vp]
+    L.pfn_head_nll.restype = c.c_int
+    L.pfn_head_nll.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp, vp, f32, c.c_int, vp]
+    L.pfn_sample.restype = c.c_int
+    L.pfn_sample.argtypes = [vp, c.c_int, vp, i64, i64, vp, u64, u64, u64, vp, i64, vp, vp, f32, c.c_int, vp]
+    L.pfn_logprob.restype = c.c_int
+    L.pfn_logprob.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp, f32, c.c_int, vp]
+    L.pfn_accept_compact.restype = c.c_int
+    L.pfn_accept_compact.argtypes = [vp, vp, i64, i64, c.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.pfn_slot_info.restype = c.c_int
+    L.pfn_slot_info.argtypes = [vp, c.c_int, c.POINTER(i64), c.POINTER(i32), c.POINTER(i32), c.POINTER(i64)]
+    L.pfn_launch_count.restype = i64
+    L.pfn_launch_count.argtypes = [vp]
+    L.pfn_kernel_times.restype = c.c_int
+    L.pfn_kernel_times.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i64), c.POINTER(c.c_double), c.c_int]
+    L.pfn_slot_export.restype = c.c_int
+    L.pfn_slot_export.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp]
+    L.pfn_debug_last_states.restype = c.c_int
+    L.pfn_debug_last_states.argtypes = [vp, vp, i64, vp]
+    _LIB = L
+    return L
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else c.c_void_p(t.data_ptr())
+
+
+def _f32_rows(t: torch.Tensor, device) -> torch.Tensor:
+    """fp32 CUDA tensor with unit inner stride (rows may be strided)."""
+    t = t.to(device=device, dtype=torch.float32)
+    if t.ndim == 1:
+        return t.contiguous()
+    if t.stride(-1) != 1 or (t.shape[0] > 1 and t.stride(0) < t.shape[1]):
+        t = t.contiguous()
+    return t
+
+
+class Engine:
+    """One `pfn_ctx`: bf16 weights, K/V-cache slots and workspace on one B200."""
+
+    def __init__(self, weights: Optional[PFNWeights] = None, device: Optional[int] = None, max_slots: int = 16,
+                 softmax_temperature: float = 0.9, chunk_rows: int = 0):
+        if not torch.cuda.is_available():
+            raise RuntimeError("npe_pfn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.lib = load_library()
+        self.weights = weights or PFNWeights.default()
+        cfg: PFNConfig = self.weights.cfg
+        self.cfg = cfg
+        self.device_index = torch.cuda.current_device() if device is None else int(device)
+        self.device = torch.device("cuda", self.device_index)
+        self.max_slots = max_slots
+        self.temperature = float(softmax_temperature)
+        mc = pfn_model_config(cfg.emsize, cfg.nhead, cfg.nlayers, cfg.nhid, cfg.num_buckets, cfg.max_groups, max_slots,
+                              chunk_rows, cfg.ln_eps, self.temperature)
+        blob = self.weights.to_blob().to(self.device)
+        h = c.c_void_p()
+        rc = self.lib.pfn_ctx_create(c.byref(mc), _ptr(blob), blob.numel(), self.device_index, self._stream(),
+                                     c.byref(h))
+        self._h = h if rc == 0 else None
+        self._check(rc)
+        del blob
+
+    # ------------------------------------------------------------------
+    def _stream(self):
+        return c.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise RuntimeError("npe_pfn_b200: " + self.lib.pfn_last_error().decode())
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.pfn_ctx_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_option(self, key: str, value: int):
+        self._check(self.lib.pfn_set_option(self._h, key.encode(), int(value)))
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.pfn_launch_count(self._h))
+
+    # ------------------------------------------------------------------
+    def prefill(self, slot: int, X: torch.Tensor, y: torch.Tensor):
+        X = _f32_rows(X, self.device)
+        y = y.to(device=self.device, dtype=torch.float32).contiguous()
+        assert X.ndim == 2 and y.ndim == 1 and X.shape[0] == y.shape[0]
+        self._check(self.lib.pfn_prefill(self._h, slot, _ptr(X), X.stride(0) if X.shape[0] > 1 else X.shape[1],
+                                         _ptr(y), X.shape[0], X.shape[1], self._stream()))
+
+    def prefill_joint(self, slot: int, joint: torch.Tensor, n_features: int):
+        """context = joint[:, :n_features], target = joint[:, n_features] (no copies of X)."""
+        assert joint.is_cuda and joint.dtype == torch.float32 and joint.stride(1) == 1
+        y = joint[:, n_features].contiguous()
+        self._check(self.lib.pfn_prefill(self._h, slot, _ptr(joint), joint.stride(0), _ptr(y), joint.shape[0],
+                                         n_features, self._stream()))
+
+    def forward_logits(self, slot: int, X: torch.Tensor) -> torch.Tensor:
+        X = _f32_rows(X, self.device)
+        M = X.shape[0]
+        out = torch.empty(M, self.cfg.num_buckets, dtype=torch.float32, device=self.device)
+        self._check(self.lib.pfn_forward_logits(self._h, slot, _ptr(X), X.stride(0) if M > 1 else X.shape[1], M,
+                                                _ptr(out), out.stride(0), self._stream()))
+        return out
+
+    def head_sample(self, slot: int, logits: torch.Tensor, M: Optional[int] = None, uniforms=None, seed=0, row0=0,
+                    offset=0, out_theta=None, ld_theta=1, with_log_prob=False, out_logp=None, eps=1e-15,
+                    accumulate=False, return_bins=False, bins=None):
+        """logits [M, B] (or a single row broadcast to M rows when `M` is given and logits.shape[0] == 1)."""
+        logits = logits.to(self.device, torch.float32)
+        assert logits.stride(-1) == 1
+        if M is None:
+            M = logits.shape[0]
+            ld = logits.stride(0)
+        else:
+            assert logits.shape[0] == 1 or logits.shape[0] == M
+            ld = 0 if logits.shape[0] == 1 and M != 1 else logits.stride(0)
+        if out_theta is None:
+            out_theta = torch.empty(M, dtype=torch.float32, device=self.device)
+            ld_theta = 1
+        if bins is None and return_bins:
+            bins = torch.empty(M, dtype=torch.int32, device=self.device)
+        if with_log_prob and out_logp is None:
+            out_logp = torch.zeros(M, dtype=torch.float32, device=self.device)
+        if uniforms is not None:
+            uniforms = uniforms.to(self.device, torch.float32).contiguous()
+        self._check(self.lib.pfn_head_sample(self._h, slot, _ptr(logits), ld, M, _ptr(uniforms), seed, row0, offset,
+                                             _ptr(out_theta), ld_theta, _ptr(bins), None, _ptr(out_logp), eps,
+                                             int(accumulate), self._stream()))
+        return out_theta, bins, out_logp
+
+    def head_nll(self, slot: int, logits: torch.Tensor, y: torch.Tensor, eps=1e-15):
+        logits = logits.to(self.device, torch.float32)
+        y = y.to(self.device, torch.float32).contiguous()
+        M = logits.shape[0]
+        out = torch.empty(M, dtype=torch.float32, device=self.device)
+        self._check(self.lib.pfn_head_nll(self._h, slot, _ptr(logits), logits.stride(0), M, _ptr(y), 1, _ptr(out), None,
+                                          eps, 0, self._stream()))
+        return out
+
+    def sample_step(self, slot: int, joint: torch.Tensor, n_features: int, out_col: int, uniforms=None, seed=0, row0=0,
+                    offset=0, out_logp=None, eps=1e-15, accumulate=True, bins=None):
+        """Fused step on the rows of `joint` [M, >= n_features+1] (fp32 CUDA, unit inner stride): reads features
+        joint[:, :n_features], writes the draw into joint[:, out_col]."""
+        assert joint.is_cuda and joint.dtype == torch.float32 and joint.stride(1) == 1
+        M = joint.shape[0]
+        ld = joint.stride(0)
+        out_ptr = c.c_void_p(joint.data_ptr() + 4 * out_col)
+        self._check(self.lib.pfn_sample(self._h, slot, _ptr(joint), ld, M, _ptr(uniforms), seed, row0, offset, out_ptr,
+                                        ld, _ptr(bins), _ptr(out_logp), eps, int(accumulate), self._stream()))
+
+    def logprob_step(self, slot: int, joint: torch.Tensor, n_features: int, y_col: int, out_logp: torch.Tensor,
+                     eps=1e-15, accumulate=True):
+        assert joint.is_cuda and joint.dtype == torch.float32 and joint.stride(1) == 1
+        M = joint.shape[0]
+        ld = joint.stride(0)
+        y_ptr = c.c_void_p(joint.data_ptr() + 4 * y_col)
+        self._check(self.lib.pfn_logprob(self._h, slot, _ptr(joint), ld, M, y_ptr, ld, _ptr(out_logp), eps,
+                                         int(accumulate), self._stream()))
+
+    def accept_compact(self, theta: torch.Tensor, lo=None, hi=None, mask=None, want_rows=True):
+        """-> (idx[int64, M] (first `count` valid), rows[M, dim] or None, count (device int64 scalar))."""
+        assert theta.is_cuda and theta.dtype == torch.float32 and theta.ndim == 2 and theta.stride(1) == 1
+        M, dim = theta.shape
+        idx = torch.empty(M, dtype=torch.int64, device=self.device)
+        rows = torch.empty(M, dim, dtype=torch.float32, device=self.device) if want_rows else None
+        count = torch.zeros((), dtype=torch.int64, device=self.device)
+        lo = None if lo is None else lo.to(self.device, torch.float32).contiguous()
+        hi = None if hi is None else hi.to(self.device, torch.float32).contiguous()
+        mask = None if mask is None else mask.to(self.device, torch.uint8).contiguous()
+        self._check(self.lib.pfn_accept_compact(self._h, _ptr(theta), theta.stride(0) if M > 1 else dim, M, dim,
+                                                _ptr(lo), _ptr(hi), _ptr(mask), _ptr(idx), _ptr(rows), _ptr(count),
+                                                self._stream()))
+        return idx, rows, count
+
+    def kernel_times(self, reset: bool = True):
+        """{class: (ms, launches, flops)} of the launches recorded while option "time_kernels" was on."""
+        ms, cnt, fl = (c.c_double * 4)(), (c.c_int64 * 4)(), (c.c_double * 4)()
+        self._check(self.lib.pfn_kernel_times(self._h, ms, cnt, fl, int(reset)))
+        names = ["attn_test", "attn_ctx", "gemm", "other"]
+        return {n: (ms[i], cnt[i], fl[i]) for i, n in enumerate(names)}
+
+    def slot_info(self, slot: int):
+        N, F, T, kv = c.c_int64(), c.c_int32(), c.c_int32(), c.c_int64()
+        self._check(self.lib.pfn_slot_info(self._h, slot, c.byref(N), c.byref(F), c.byref(T), c.byref(kv)))
+        return {"N": N.value, "F": F.value, "T": T.value, "kv_bytes": kv.value}
+
+    def slot_export(self, slot: int, want_kv: bool = False):
+        info = self.slot_info(slot)
+        G = info["T"] - 1
+        stats = torch.empty(3 * 2 * G, dtype=torch.float32, device=self.device)
+        ystats = torch.empty(3, dtype=torch.float32, device=self.device)
+        borders = torch.empty(self.cfg.num_buckets + 1, dtype=torch.float32, device=self.device)
+        kv = None
+        if want_kv:
+            kv = torch.empty(self.cfg.nlayers, info["T"], info["N"], 64, dtype=torch.bfloat16, device=self.device)
+        self._check(self.lib.pfn_slot_export(self._h, slot, _ptr(stats), _ptr(ystats), _ptr(borders), _ptr(kv),
+                                             self._stream()))
+        Fp = 2 * G
+        return {"mean": stats[:Fp], "std": stats[Fp:2 * Fp], "scale": stats[2 * Fp:2 * Fp + G], "y_mean": ystats[0],
+                "y_std": ystats[1], "y_fill": ystats[2], "borders": borders, "kv": kv, **info}
+
+    def last_states(self, rows: int, T: int) -> torch.Tensor:
+        out = torch.empty(rows, T, self.cfg.emsize, dtype=torch.float32, device=self.device)
+        self._check(self.lib.pfn_debug_last_states(self._h, _ptr(out), out.numel(), self._stream()))
+        return out
+
+
+_ENGINES = {}
+
+
+def get_engine(device: Optional[int] = None, weights: Optional[PFNWeights] = None, **kw) -> Engine:
+    """Process-wide engine per (device, weights identity, options)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("npe_pfn_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    dev = torch.cuda.current_device() if device is None else int(device)
+    key = (dev, id(weights) if weights is not None else None, tuple(sorted(kw.items())))
+    if key not in _ENGINES:
+        _ENGINES[key] = Engine(weights=weights, device=dev, **kw)
+    return _ENGINES[key]

@@ -1,0 +1,462 @@
+"""Posterior objects of NPE-PFN over the B200 engine.
+
+Public surface and semantics follow `/root/reference/npe_pfn/npe_pfn.py`
+(`NPE_PFN_Core` :26-600, `TabPFN_Based_NPE_PFN` :708-744): `append_simulations` (replaces the stored
+simulations, :75-82), `sample` (:253-308), `sample_batched` (:310-410), `log_prob` (:412-455),
+`get_context`, `_within_support` (:581-600), same defaults and error behaviour.
+
+What differs is underneath.  The reference re-fits the estimator for every parameter dimension of every
+proposal round and every call (`fit` at :140 sits inside `_sample`, which sits inside the rejection loop);
+here the context is prefilled ONCE per (context, dimension) into an HBM K/V cache (`pfn_prefill`) and each
+autoregressive step is one fused engine call (`pfn_sample` / `pfn_logprob`) that reads the growing joint
+matrix on the device and writes the new column in place.  Draws, log-probs and the accept/reject
+bookkeeping stay on the GPU; results are returned as CPU tensors like the reference's
+(`return_device=True` on the underscore methods keeps them on the device).
+"""
+from __future__ import annotations
+
+import math
+from typing import Literal, Mapping, Optional
+
+import torch
+from torch import Tensor
+from torch.distributions import Distribution
+
+from .accept_reject_sampler import accept_reject_sample
+from .estimator import B200TabPFNRegressor, draw_seed
+from .support_posterior import get_filtering_method
+from .utils import box_bounds_of
+
+
+class _Context:
+    """Device copy of the joint context [N, dx + dtheta] and which engine slots hold its K/V caches."""
+
+    def __init__(self, key, joint: Tensor, dim_x: int, dim_theta: int):
+        self.key = key
+        self.joint = joint
+        self.dim_x = dim_x
+        self.dim_theta = dim_theta
+
+
+class NPE_PFN_Core:
+    """TabPFN-based simulation-based inference with an SBI-like interface (npe_pfn.py:26-31)."""
+
+    def __init__(
+        self,
+        show_progress_bars: bool = False,
+        prior: Optional[Distribution] = None,
+        embedding_net: Optional[torch.nn.Module] = None,
+        x_shape: Optional[torch.Size] = None,
+        regressor_init_kwargs: Mapping = {},
+        classifier_init_kwargs: Mapping = {},
+    ) -> None:
+        self.show_progress_bars = show_progress_bars
+        self.prior = prior
+        self.regressor_init_kwargs = regressor_init_kwargs
+        self.classifier_init_kwargs = classifier_init_kwargs
+        self._model = B200TabPFNRegressor(**self.regressor_init_kwargs)
+        self._model_classifier = None
+        self.embedding_net = embedding_net
+        self.x_shape = x_shape
+        self._theta_train = None
+        self._x_train = None
+        self._ctx_version = 0
+        self._ctx: Optional[_Context] = None
+        self._prior_bounds = "unset"
+        #: extra Philox row offset (distinct per rank when draws are sharded over GPUs)
+        self.rank_row_offset = 0
+
+    # -- pickling: drop the engine-backed model, rebuild from kwargs (npe_pfn.py:57-71) --------------
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_model"] = None
+        state["_model_classifier"] = None
+        state["_ctx"] = None
+        return state
+
+    def __setstate__(self, state):
+        self.__dict__.update(state)
+        self._model = B200TabPFNRegressor(**self.regressor_init_kwargs)
+
+    # -- data -----------------------------------------------------------------------------------------
+    def append_simulations(self, theta: Tensor, x: Tensor):
+        """Store simulations (REPLACES earlier ones, like npe_pfn.py:75-82) and invalidate the K/V caches."""
+        self._theta_train = None
+        self._x_train = None
+        if self.embedding_net:
+            x = x.reshape(-1, *self.x_shape)
+            x = self.embedding_net(x)
+        self._theta_train = self._validate_theta(theta)
+        self._x_train = self._validate_x(x)
+        self._ctx_version += 1
+        self._ctx = None
+        return self
+
+    def get_context(self, x: Tensor):
+        return self._theta_train, self._x_train
+
+    def _context_key(self, x: Tensor):
+        return (self._ctx_version,)
+
+    def _validate_x(self, x: Tensor):
+        if x is None:
+            raise NotImplementedError("Setting a default x is not yet supported.")
+        x = x.unsqueeze(0) if x.ndim == 1 else x
+        assert x.ndim == 2, "x must be a 2D tensor."
+        if self._x_train is not None:
+            assert x.shape[1] == self._x_train.shape[1], "The number of features in x must match the training data."
+        return x
+
+    def _validate_theta(self, theta: Tensor):
+        theta = theta.unsqueeze(0) if theta.ndim == 1 else theta
+        assert theta.ndim == 2, "theta must be a 2D tensor."
+        if self._theta_train is not None:
+            assert theta.shape[1] == self._theta_train.shape[1], \
+                "The number of features in theta must match the training data."
+        return theta
+
+    # -- engine plumbing ------------------------------------------------------------------------------
+    @property
+    def engine(self):
+        return self._model.engine
+
+    def _prepare_context(self, x: Tensor, use_filter: bool = True) -> _Context:
+        key = self._context_key(x) if use_filter else ("all", self._ctx_version)
+        if self._ctx is not None and key is not None and self._ctx.key == key:
+            return self._ctx
+        if use_filter:
+            theta_context, x_context = self.get_context(x)
+        else:
+            theta_context, x_context = self._theta_train, self._x_train
+        dev = self.engine.device
+        joint = torch.cat([x_context.to(torch.float32), theta_context.to(torch.float32)], dim=1).to(dev).contiguous()
+        self._ctx = _Context(key if key is not None else object(), joint, x_context.shape[1], theta_context.shape[1])
+        return self._ctx
+
+    def _ensure_slot(self, ctx: _Context, d: int) -> int:
+        """Slot holding the K/V cache of (ctx, d); prefilled on first use, shared engine slots are tagged."""
+        eng = self.engine
+        slot = d % eng.max_slots
+        tag = (id(self), ctx.key, d)
+        tags = eng.__dict__.setdefault("_slot_tags", {})
+        if tags.get(slot) != tag:
+            eng.prefill_joint(slot, ctx.joint, ctx.dim_x + d)
+            tags[slot] = tag
+        return slot
+
+    def prefill(self, x: Tensor):
+        """Build the K/V caches of every dimension for the context of `x` now (otherwise done lazily)."""
+        x = self._validate_x(x)
+        ctx = self._prepare_context(x)
+        for d in range(ctx.dim_theta):
+            self._ensure_slot(ctx, d)
+        return self
+
+    def invalidate_cache(self):
+        self._ctx = None
+        self.engine.__dict__.pop("_slot_tags", None)
+
+    # -- hot loops ----------------------------------------------------------------------------------------
+    def _sample(self, sampling_batch_size: int, x: Tensor, repeat_x: bool = True, with_log_prob: bool = False,
+                eps=1e-15, uniforms: Optional[Tensor] = None, seed: Optional[int] = None, return_device: bool = False,
+                return_bins: bool = False, use_filter: bool = True):
+        """Autoregressive draw of theta | x for one observation (npe_pfn.py:111-169).
+
+        `uniforms[M, dim_theta]` may be injected (parity tests); otherwise Philox4x32-10 keyed by a seed taken
+        from torch's global generator, counter = (row, dimension)."""
+        ctx = self._prepare_context(x, use_filter)
+        eng = self.engine
+        dev = eng.device
+        dx, dth = ctx.dim_x, ctx.dim_theta
+        xd = x.to(dev, torch.float32)
+        if repeat_x:
+            M = int(sampling_batch_size)
+        else:
+            M = xd.shape[0]
+        buf = torch.empty(M, dx + dth, dtype=torch.float32, device=dev)
+        buf[:, :dx] = xd
+        lp = torch.zeros(M, dtype=torch.float32, device=dev) if with_log_prob else None
+        bins = torch.empty(dth, M, dtype=torch.int32, device=dev) if return_bins else None
+        if uniforms is not None:
+            uniforms = uniforms.to(dev, torch.float32).t().contiguous()  # [dth, M]
+        elif seed is None:
+            seed = draw_seed()
+        row0 = self.rank_row_offset
+        for d in range(dth):
+            slot = self._ensure_slot(ctx, d)
+            u_d = uniforms[d] if uniforms is not None else None
+            b_d = bins[d] if bins is not None else None
+            if d == 0 and repeat_x and M > 1 and xd.shape[0] == 1:
+                # every test row is the same observation: one forward row, M inverse-CDF draws from its logits
+                logits = eng.forward_logits(slot, buf[:1, :dx])
+                eng.head_sample(slot, logits, M=M, uniforms=u_d, seed=seed or 0, row0=row0, offset=d,
+                                out_theta=buf[:, dx], ld_theta=buf.stride(0), out_logp=lp, eps=eps, accumulate=True,
+                                bins=b_d)
+            else:
+                eng.sample_step(slot, buf, dx + d, dx + d, uniforms=u_d, seed=seed or 0, row0=row0, offset=d,
+                                out_logp=lp, eps=eps, accumulate=True, bins=b_d)
+        theta = buf[:, dx:]
+        if not return_device:
+            theta = theta.cpu()
+            lp = lp.cpu() if lp is not None else None
+        if return_bins:
+            return theta, lp, bins.t()
+        return theta, lp
+
+    def _sample_batched(self, x: Tensor, num_samples_per_obs: int, with_log_prob: bool = False, eps: float = 1e-15,
+                        return_device: bool = False, seed: Optional[int] = None):
+        """All observations against one shared, unfiltered context (npe_pfn.py:171-251):
+        -> theta [num_obs, n, dim_theta], log_probs [num_obs, n] | None."""
+        num_obs = x.shape[0]
+        n = int(num_samples_per_obs)
+        ctx = self._prepare_context(x, use_filter=False)
+        eng = self.engine
+        dev = eng.device
+        dx, dth = ctx.dim_x, ctx.dim_theta
+        xd = x.to(dev, torch.float32)
+        M = num_obs * n
+        buf = torch.empty(M, dx + dth, dtype=torch.float32, device=dev)
+        buf[:, :dx] = xd.repeat_interleave(n, dim=0)
+        lp = torch.zeros(M, dtype=torch.float32, device=dev) if with_log_prob else None
+        if seed is None:
+            seed = draw_seed()
+        row0 = self.rank_row_offset
+        for d in range(dth):
+            slot = self._ensure_slot(ctx, d)
+            if d == 0 and n > 1:
+                # rows of one observation share their features: num_obs forward rows, n draws from each
+                logits = eng.forward_logits(slot, xd)
+                for o in range(num_obs):
+                    eng.head_sample(slot, logits[o:o + 1], M=n, seed=seed, row0=row0 + o * n, offset=0,
+                                    out_theta=buf[o * n:(o + 1) * n, dx], ld_theta=buf.stride(0),
+                                    out_logp=lp[o * n:(o + 1) * n] if lp is not None else None, eps=eps,
+                                    accumulate=True)
+            else:
+                eng.sample_step(slot, buf, dx + d, dx + d, seed=seed, row0=row0, offset=d, out_logp=lp, eps=eps,
+                                accumulate=True)
+        theta = buf[:, dx:].reshape(num_obs, n, dth)
+        if lp is not None:
+            lp = lp.reshape(num_obs, n)
+        if not return_device:
+            theta = theta.cpu()
+            lp = lp.cpu() if lp is not None else None
+        return theta, lp
+
+    def _autoregressive_log_prob(self, theta: Tensor, x: Tensor = None, repeat_x: bool = True, eps: float = 1e-15,
+                                 return_device: bool = False) -> Tensor:
+        """sum_d log p(theta_d | x, theta_<d), teacher forced (npe_pfn.py:462-524); -inf -> log(eps) per dim."""
+        ctx = self._prepare_context(x)
+        eng = self.engine
+        dev = eng.device
+        dx, dth = ctx.dim_x, ctx.dim_theta
+        m = theta.shape[0]
+        xd = x.to(dev, torch.float32)
+        if not repeat_x:
+            assert xd.shape[0] == m
+        buf = torch.empty(m, dx + dth, dtype=torch.float32, device=dev)
+        buf[:, :dx] = xd
+        buf[:, dx:] = theta.to(dev, torch.float32)
+        lp = torch.zeros(m, dtype=torch.float32, device=dev)
+        for d in range(dth):
+            slot = self._ensure_slot(ctx, d)
+            eng.logprob_step(slot, buf, dx + d, dx + d, lp, eps=eps, accumulate=True)
+        return lp if return_device else lp.cpu()
+
+    # -- public API -----------------------------------------------------------------------------------------
+    def sample(self, sample_shape: torch.Size = torch.Size(), x: Tensor = None, max_sampling_batch_size: int = 10_000,
+               with_log_prob: bool = False, eps=1e-15, max_iter_rejection: int | None = None,
+               show_progress_bars: bool = False) -> Tensor | tuple[Tensor, Tensor]:
+        """Sample p(theta | x) for ONE observation with prior-support rejection (npe_pfn.py:253-308)."""
+        if self.embedding_net:
+            x = x.reshape(-1, *self.x_shape)
+            x = self.embedding_net(x)
+        x = self._validate_x(x)
+        if x.shape[0] > 1:
+            raise ValueError(".sample() supports only `batchsize == 1`. If you intend "
+                             "to sample multiple observations, use `.sample_batched()`. ")
+
+        def proposal_fn(batch_size, **kwargs):
+            return self._sample(batch_size, x, repeat_x=True, with_log_prob=with_log_prob, eps=eps,
+                                return_device=True)
+
+        samples, log_probs, _ar = accept_reject_sample(
+            proposal=proposal_fn,
+            accept_reject_fn=_SupportCheck(self),
+            num_samples=torch.Size(sample_shape).numel(),
+            show_progress_bars=self.show_progress_bars,
+            max_sampling_batch_size=max_sampling_batch_size,
+            proposal_sampling_kwargs={},
+            max_iter_rejection=max_iter_rejection,
+        )
+        self.last_acceptance_rate = _ar
+        samples = samples.cpu()
+        if with_log_prob:
+            return samples, log_probs.cpu()
+        return samples
+
+    def sample_batched(self, x: Tensor, sample_shape: torch.Size = torch.Size(), max_sampling_batch_size: int = 10_000,
+                       with_log_prob: bool = False, eps: float = 1e-15, oversample_factor: float = 1.5,
+                       show_progress_bars: bool = False) -> Tensor | tuple[Tensor, Tensor]:
+        """Sample p(theta | x_i) for many observations sharing one unfiltered context (npe_pfn.py:310-410):
+        oversample by `oversample_factor`, at most 10 rounds, per observation keep the first in-support draws.
+        `max_sampling_batch_size` is accepted and unused, like the reference (Appendix B.6)."""
+        if self.embedding_net:
+            x = x.reshape(-1, *self.x_shape)
+            x = self.embedding_net(x)
+        x = self._validate_x(x)
+        num_obs = x.shape[0]
+        num_samples = torch.Size(sample_shape).numel()
+
+        if self.prior is None:
+            samples, log_probs = self._sample_batched(x, num_samples, with_log_prob=with_log_prob, eps=eps)
+            return (samples, log_probs) if with_log_prob else samples
+
+        num_to_sample = int(num_samples * oversample_factor)
+        dev = self.engine.device
+        dth = self._theta_train.shape[1]
+        out = torch.empty(num_obs, num_samples, dth, dtype=torch.float32, device=dev)
+        out_lp = torch.empty(num_obs, num_samples, dtype=torch.float32, device=dev) if with_log_prob else None
+        filled = torch.zeros(num_obs, dtype=torch.long, device=dev)
+        obs_index = torch.arange(num_obs, device=dev)[:, None]
+        max_iter = 10
+        for _iteration in range(max_iter):
+            if bool((filled >= num_samples).all()):
+                break
+            raw, raw_lp = self._sample_batched(x, num_to_sample, with_log_prob=with_log_prob, eps=eps,
+                                               return_device=True)
+            valid = self._within_support_device(raw.reshape(-1, dth)).reshape(num_obs, num_to_sample)
+            rank = torch.cumsum(valid.long(), dim=1)  # 1-based position among this round's valid draws
+            take = valid & (rank <= (num_samples - filled)[:, None])
+            dst = (filled[:, None] + rank - 1).clamp_(0, num_samples - 1)
+            oi = obs_index.expand_as(dst)[take]
+            out[oi, dst[take]] = raw[take]
+            if with_log_prob:
+                out_lp[oi, dst[take]] = raw_lp[take]
+            filled = filled + take.sum(dim=1)
+        if not bool((filled >= num_samples).all()):
+            raise RuntimeError("sample_batched: some observations have fewer than num_samples in-support draws "
+                               "after 10 rounds (the reference fails here when stacking ragged results)")
+        if with_log_prob:
+            return out.cpu(), out_lp.cpu()
+        return out.cpu()
+
+    def log_prob(self, theta: Tensor, x: Tensor, max_sampling_batch_size: int = 10_000, mode="autoregressive",
+                 eps=1e-15, **ratio_kwargs):
+        """log p(theta | x) in chunks of `max_sampling_batch_size` (npe_pfn.py:412-455); CPU result."""
+        if self.embedding_net:
+            x = x.reshape(-1, *self.x_shape)
+            x = self.embedding_net(x)
+        theta = self._validate_theta(theta)
+        x = self._validate_x(x)
+        log_probs = torch.zeros(theta.shape[0])
+        for i in range(0, theta.shape[0], max_sampling_batch_size):
+            if mode == "autoregressive":
+                log_probs[i:i + max_sampling_batch_size] = self._autoregressive_log_prob(
+                    theta[i:i + max_sampling_batch_size], x, eps=eps)
+            elif mode == "ratio_based":
+                log_probs[i:i + max_sampling_batch_size] = self._ratio_based_log_prob(
+                    theta[i:i + max_sampling_batch_size], x, eps=eps, **ratio_kwargs)
+            else:
+                raise ValueError(f"Invalid mode: {mode}")
+        return log_probs
+
+    def log_prob_batched(self, theta: Tensor, x: Tensor):
+        raise NotImplementedError
+
+    def _ratio_based_log_prob(self, theta: Tensor, x: Tensor = None, **kwargs) -> Tensor:
+        raise NotImplementedError(
+            "ratio_based log_prob needs the TabPFN classifier head (npe_pfn.py:526-570, 603-704); it is listed as "
+            "the next row after the regressor path in DESIGN.md. Use mode='autoregressive'.")
+
+    def _get_classifier_bounds(self):
+        if self._model_classifier is None:
+            return None, None
+        return self._model_classifier._padded_dim_min, self._model_classifier._padded_dim_max
+
+    # -- support ----------------------------------------------------------------------------------------------
+    def _within_support(self, theta: Tensor) -> Tensor:
+        """`prior.support.check` (all dims) or finite `prior.log_prob` (npe_pfn.py:581-600)."""
+        try:
+            sample_check = self.prior.support.check(theta)
+            if sample_check.shape == theta.shape:
+                sample_check = torch.all(sample_check, dim=-1)
+            return sample_check
+        except (NotImplementedError, AttributeError):
+            return torch.isfinite(self.prior.log_prob(theta))
+
+    def _bounds(self):
+        if self._prior_bounds == "unset":
+            self._prior_bounds = box_bounds_of(self.prior) if self.prior is not None else None
+        return self._prior_bounds
+
+    def _within_support_device(self, theta: Tensor) -> Tensor:
+        """Support mask for CUDA draws without leaving the device when the support is a box / all of R^d."""
+        b = self._bounds()
+        if b is None:
+            return self._within_support(theta.cpu()).to(theta.device)
+        lo, hi = b
+        ok = torch.isfinite(theta).all(dim=-1)
+        if lo is not None:
+            ok &= (theta >= lo.to(theta.device)).all(dim=-1)
+        if hi is not None:
+            ok &= (theta <= hi.to(theta.device)).all(dim=-1)
+        return ok
+
+
+class _SupportCheck:
+    """accept/reject callable handed to `accept_reject_sample`: plain mask on CPU tensors (reference
+    behaviour) and `compact()` = fused support check + ordered stream compaction for device tensors."""
+
+    def __init__(self, posterior: NPE_PFN_Core):
+        self.p = posterior
+
+    def __call__(self, theta: Tensor) -> Tensor:
+        if theta.is_cuda:
+            return self.p._within_support_device(theta)
+        return self.p._within_support(theta)
+
+    def compact(self, theta: Tensor, log_probs: Optional[Tensor]):
+        p = self.p
+        b = p._bounds()
+        theta = theta.contiguous()
+        if b is None:
+            mask = p._within_support(theta.cpu()).to(theta.device)
+            idx, rows, count = p.engine.accept_compact(theta, mask=mask)
+        else:
+            idx, rows, count = p.engine.accept_compact(theta, lo=b[0], hi=b[1])
+        k = int(count.item())  # the one host sync per rejection round (accept_reject_sampler.py:62)
+        kept_lp = log_probs[idx[:k]] if log_probs is not None else None
+        return rows[:k], kept_lp, k
+
+
+# NOTE: can never support batched sampling with filtering, as the context depends on x (npe_pfn.py:707)
+class TabPFN_Based_NPE_PFN(NPE_PFN_Core):
+    def __init__(
+        self,
+        show_progress_bars: bool = False,
+        prior: Optional[Distribution] = None,
+        filter_type: (Literal["latest_filtering", "random_filtering", "standardized_euclidean_filtering"]
+                      | callable) = "standardized_euclidean_filtering",
+        filter_context_size: int = 10_000,
+        regressor_init_kwargs: Mapping = {},
+        classifier_init_kwargs: Mapping = {},
+        embedding_net: Optional[torch.nn.Module] = None,
+        x_shape: Optional[torch.Size] = None,
+    ):
+        super().__init__(show_progress_bars, prior, regressor_init_kwargs=regressor_init_kwargs,
+                         classifier_init_kwargs=classifier_init_kwargs, embedding_net=embedding_net, x_shape=x_shape)
+        self.filter_type = filter_type
+        self.filter = get_filtering_method(filter_type)
+        self.filter_context_size = filter_context_size
+
+    def get_context(self, x: Tensor):
+        x = self._validate_x(x)
+        return self.filter(x, self._theta_train, self._x_train, self.filter_context_size)
+
+    def _context_key(self, x: Tensor):
+        if self.filter_type == "random_filtering" or callable(self.filter_type):
+            return None  # context changes from call to call: never reuse a cache
+        if self.filter_type in ("no_filtering", "latest_filtering"):
+            return (self._ctx_version, self.filter_type, self.filter_context_size)
+        xb = x.detach().to("cpu", torch.float32).contiguous().numpy().tobytes()
+        return (self._ctx_version, self.filter_type, self.filter_context_size, xb)

@@ -1,0 +1,343 @@
+"""GPU parity tests (`-m gpu`): the CUDA path, called through the C-ABI (ctypes), against the CPU oracle on the
+same seeded inputs, against the frozen golden vectors, and through size-independent properties at larger sizes.
+
+Tolerances (stated, see DESIGN.md "parity"): integer / index work (bucket search, Philox, compaction) is
+bit-exact given identical logits and uniforms; the transformer runs bf16 operands with fp32 accumulation against
+the oracle's fp32, so logits are compared with |dlogit| <= LOGIT_ATOL (max) and per-dimension log-prob with
+|dlogp| <= LOGP_ATOL.
+"""
+import math
+import os
+import pickle
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 0.12      # max |logit_cuda - logit_oracle| (logits have std ~1.5)
+LOGIT_MEAN_ATOL = 0.02
+LOGP_ATOL = 0.06       # per dimension
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "oracle_golden.pt")
+
+
+def _toy(N, dx, dth, seed):
+    """theta ~ N(0, I), x = theta W^T + 0.1 eps + 1 (generator of /root/reference/tests/test_npe_pfn.py:47-55)."""
+    g = torch.Generator().manual_seed(seed)
+    theta = torch.randn(N, dth, generator=g)
+    w = torch.randn(dx, dth, generator=g)
+    x = theta @ w.T + 0.1 * torch.randn(N, dx, generator=g) + 1.0
+    return theta, x, g
+
+
+def test_library_loaded_and_abi(engine):
+    from npe_pfn_b200.engine import ABI_SYMBOLS, load_library
+    L = load_library()
+    assert L.pfn_abi_version() == 1
+    for s in ABI_SYMBOLS:
+        assert hasattr(L, s)
+    assert engine.launch_count >= 1
+
+
+@pytest.mark.parametrize("F,N", [(1, 16), (2, 33), (3, 100), (5, 257), (10, 300)])
+def test_fit_statistics_and_borders(engine, weights, F, N):
+    from oracle import bar_head
+    from oracle import tabpfn_oracle as model
+    from oracle.estimator import y_standardise
+    g = torch.Generator().manual_seed(N)
+    X = torch.randn(N, F, generator=g) * 3 + 1
+    if F >= 3:
+        X[1, 1] = float("nan")
+        X[2, 2] = float("inf")
+    y = torch.randn(N, generator=g) * 2 - 0.5
+    engine.prefill(0, X, y)
+    ex = engine.slot_export(0)
+    ym, ys, yz = y_standardise(y)
+    st = model.EncoderStats(X, yz, (F + 1) // 2)
+    assert torch.allclose(ex["mean"].cpu(), st.mean, atol=1e-6, rtol=1e-6)
+    assert torch.allclose(ex["std"].cpu(), st.std, atol=1e-6, rtol=1e-6)
+    assert torch.equal(ex["scale"].cpu(), st.scale)
+    assert abs(float(ex["y_mean"]) - ym) <= 1e-6 * max(1, abs(ym)) and abs(float(ex["y_std"]) - ys) <= 1e-6 * ys
+    assert abs(float(ex["y_fill"]) - float(st.y_fill)) < 1e-6
+    if float(ex["y_mean"]) == ym and float(ex["y_std"]) == ys:
+        assert torch.equal(ex["borders"].cpu(), bar_head.renorm_borders(weights.borders, ym, ys))
+    assert ex["N"] == N and ex["F"] == F and ex["T"] == (F + 1) // 2 + 1
+
+
+@pytest.mark.parametrize("F,N,M", [(1, 16, 8), (2, 64, 50), (3, 100, 33), (5, 200, 130), (10, 300, 64), (19, 150, 40)])
+def test_logits_and_kv_cache_vs_oracle(engine, weights, F, N, M):
+    from oracle.estimator import OracleTabPFNRegressor
+    g = torch.Generator().manual_seed(F * 1000 + N)
+    Xc = torch.randn(N, F, generator=g)
+    yc = Xc[:, 0] * 0.8 + 0.2 * torch.randn(N, generator=g)
+    Xt = torch.randn(M, F, generator=g)
+    if F >= 3:
+        Xc[0, 1] = float("nan")
+        Xt[0, 2] = float("-inf")
+    oracle = OracleTabPFNRegressor(weights=weights).fit(Xc, yc)
+    ref = oracle.predict(Xt)["logits"]
+    engine.prefill(1, Xc, yc)
+    got = engine.forward_logits(1, Xt).cpu()
+    d = (got - ref).abs()
+    print(f"F={F} N={N}: max|dlogit|={d.max():.4f} mean={d.mean():.5f} ref std={ref.std():.3f}")
+    assert d.max() <= LOGIT_ATOL and d.mean() <= LOGIT_MEAN_ATOL
+    # K/V cache of the context (bf16) against the oracle's fp32 head-0 K/V
+    kv = engine.slot_export(1, want_kv=True)["kv"].float().cpu()  # [L, T, N, 64]
+    for l in (0, weights.cfg.nlayers - 1):
+        k_ref, v_ref = oracle.cache.k0[l], oracle.cache.v0[l]  # [T, N, 32]
+        assert (kv[l, :, :, :32] - k_ref).abs().max() <= 0.08
+        assert (kv[l, :, :, 32:] - v_ref).abs().max() <= 0.08
+
+
+def test_golden_vectors_cuda(engine, weights):
+    gold = torch.load(GOLDEN)
+    for case in gold["cases"]:
+        engine.prefill(2, case["Xc"], case["yc"])
+        got = engine.forward_logits(2, case["Xt"]).cpu()
+        d = (got[:, case["cols"]] - case["logits_cols"]).abs()
+        assert d.max() <= LOGIT_ATOL, (case["F"], d.max())
+        assert (torch.logsumexp(got, -1) - case["lse"]).abs().max() <= LOGIT_ATOL
+        # head on the GOLDEN logits row: identical bucket and sample, bit for bit
+        th, bins, _ = engine.head_sample(2, case["logits_full0"], uniforms=case["u"][:1], return_bins=True)
+        assert int(bins[0]) == int(case["idx0"]) and float(th[0]) == float(case["theta0"])
+
+
+@pytest.mark.parametrize("M,B_scale", [(1, 1.0), (257, 3.0), (4096, 0.3)])
+def test_head_bit_exact_vs_oracle(engine, weights, M, B_scale):
+    from oracle import bar_head
+    g = torch.Generator().manual_seed(M)
+    B = weights.cfg.num_buckets
+    logits = torch.randn(M, B, generator=g) * B_scale
+    if M > 4:
+        logits[3, :100] = -float("inf")
+        logits[4] = 0.0
+    u = torch.rand(M, generator=g)
+    yv = torch.randn(200, generator=g)
+    engine.prefill(3, torch.randn(200, 2, generator=g), yv * 1.7 + 0.3)
+    borders = engine.slot_export(3)["borders"].cpu()
+    th, bins, lp = engine.head_sample(3, logits, uniforms=u, return_bins=True, with_log_prob=True)
+    th_ref, idx_ref, _ = bar_head.sample(logits, borders, uniforms=u)
+    assert torch.equal(bins.cpu(), idx_ref)
+    assert torch.equal(th.cpu(), th_ref)
+    nll_ref = bar_head.nll(logits, borders, th_ref)
+    assert torch.allclose(-lp.cpu(), nll_ref, atol=2e-5, rtol=1e-5)
+    # Philox path: same uniforms as the oracle's generator, hence same draws
+    th2, bins2, _ = engine.head_sample(3, logits, seed=1234567, row0=10, offset=3, return_bins=True)
+    th2_ref, idx2_ref, _ = bar_head.sample(logits, borders, seed=1234567, row0=10, offset=3)
+    assert torch.equal(bins2.cpu(), idx2_ref) and torch.equal(th2.cpu(), th2_ref)
+    # negative log density on given targets, including both half-normal tails
+    y = torch.cat([torch.linspace(borders[0].item() - 2, borders[-1].item() + 2, M - 1), borders[5:6]])[:M] \
+        if M > 1 else borders[7:8]
+    nll = engine.head_nll(3, logits, y).cpu()
+    assert torch.allclose(nll, bar_head.nll(logits, borders, y), atol=2e-5, rtol=1e-5)
+    # broadcast of a single logits row to many draws
+    th3, bins3, _ = engine.head_sample(3, logits[:1], M=64, uniforms=torch.linspace(0.01, 0.99, 64), return_bins=True)
+    th3_ref, idx3_ref, _ = bar_head.sample(logits[:1].expand(64, B).contiguous(), borders,
+                                           uniforms=torch.linspace(0.01, 0.99, 64))
+    assert torch.equal(bins3.cpu(), idx3_ref) and torch.equal(th3.cpu(), th3_ref)
+    assert torch.all(th3[1:] >= th3[:-1])  # inverse CDF is monotone in u
+
+
+def test_fused_sampling_vs_reference_loop(engine, weights):
+    """`_sample` with injected uniforms against the oracle's restatement of npe_pfn.py:111-169."""
+    from npe_pfn_b200 import NPE_PFN_Core
+    from oracle.estimator import OracleTabPFNRegressor
+    from oracle.reference_loop import sample_loop
+    theta, x, g = _toy(120, 3, 3, 7)
+    xo = x[:1].clone()
+    M = 96
+    u = torch.rand(M, 3, generator=g)
+    post = NPE_PFN_Core(regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    s, lp, bins = post._sample(M, xo, with_log_prob=True, uniforms=u, return_bins=True)
+    s_ref, lp_ref, bins_ref = sample_loop(OracleTabPFNRegressor(weights=weights), x, theta, xo, M,
+                                          with_log_prob=True, uniforms=u, return_bins=True)
+    same0 = bins[:, 0].cpu() == bins_ref[:, 0]
+    dbin = (bins.cpu() - bins_ref).abs()
+    print("bucket mismatch rate per dim:", (dbin != 0).float().mean(0).tolist(), "max |dbin|", dbin.max().item())
+    assert same0.float().mean() >= 0.9
+    # where the first-dimension bucket agrees the sample agrees to within the bucket width
+    assert (s[:, 0] - s_ref[:, 0]).abs()[same0].max() < 5e-3
+    # draws are the same distribution: compare per-dimension means / stds loosely
+    assert (s.mean(0) - s_ref.mean(0)).abs().max() < 0.15
+    assert (lp - lp_ref).abs().median() < 3 * LOGP_ATOL
+
+
+def test_log_prob_vs_reference_loop(engine, weights):
+    from npe_pfn_b200 import NPE_PFN_Core
+    from oracle.estimator import OracleTabPFNRegressor
+    from oracle.reference_loop import logprob_loop
+    theta, x, g = _toy(150, 4, 3, 9)
+    xo = x[:1].clone()
+    th = torch.randn(80, 3, generator=g)
+    th[0] = 50.0  # far outside: half-normal tail / clamp path
+    post = NPE_PFN_Core(regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    lp = post.log_prob(th, xo)
+    lp_ref = logprob_loop(OracleTabPFNRegressor(weights=weights), x, theta, xo, th)
+    d = (lp - lp_ref).abs()
+    print(f"max |dlogp| = {d.max():.4f} (3 dims)")
+    assert lp.shape == (80,) and torch.isfinite(lp).all()
+    assert d.max() <= 3 * LOGP_ATOL
+    # chunked evaluation (max_sampling_batch_size) gives the same numbers
+    lp_chunked = post.log_prob(th, xo, max_sampling_batch_size=17)
+    assert torch.allclose(lp, lp_chunked, atol=1e-5)
+
+
+def test_accept_compact_matches_torch(engine):
+    g = torch.Generator().manual_seed(3)
+    for M, dim in [(1, 2), (255, 3), (256, 1), (100_003, 5)]:
+        th = (torch.rand(M, dim, generator=g) * 4 - 2).cuda()
+        if M > 10:
+            th[7, 0] = float("nan")
+        lo = torch.full((dim,), -1.0)
+        hi = torch.full((dim,), 1.5)
+        idx, rows, count = engine.accept_compact(th, lo=lo, hi=hi)
+        ok = ((th >= lo.cuda()) & (th <= hi.cuda())).all(1) & torch.isfinite(th).all(1)
+        k = int(count)
+        assert k == int(ok.sum())
+        assert torch.equal(idx[:k], torch.nonzero(ok).squeeze(1))
+        assert torch.equal(rows[:k], th[ok])
+    # mask-only form, empty input and all-rejected
+    th = torch.randn(1000, 2, generator=g).cuda()
+    mask = (torch.arange(1000) % 3 == 0)
+    idx, rows, count = engine.accept_compact(th, mask=mask)
+    assert int(count) == int(mask.sum()) and torch.equal(rows[:int(count)], th[mask.cuda()])
+    idx, rows, count = engine.accept_compact(th, lo=torch.full((2,), 100.0), hi=torch.full((2,), 101.0))
+    assert int(count) == 0
+    idx, rows, count = engine.accept_compact(torch.empty(0, 2, device="cuda"))
+    assert int(count) == 0
+
+
+def test_rows_independent_and_chunk_invariant(engine):
+    """Size-independent properties at a larger context: permuting / re-chunking test rows does not change a row."""
+    g = torch.Generator().manual_seed(21)
+    N, F, M = 2000, 7, 3000
+    Xc = torch.randn(N, F, generator=g)
+    yc = Xc.sum(1) + 0.1 * torch.randn(N, generator=g)
+    Xt = torch.randn(M, F, generator=g)
+    engine.prefill(4, Xc, yc)
+    a = engine.forward_logits(4, Xt)
+    perm = torch.randperm(M, generator=g)
+    b = engine.forward_logits(4, Xt[perm])
+    assert torch.equal(a[perm.cuda()], b)
+    engine.set_option("chunk_rows", 1000)
+    try:
+        c = engine.forward_logits(4, Xt)
+    finally:
+        engine.set_option("chunk_rows", 0)
+    assert torch.equal(a, c)
+    assert torch.isfinite(a).all()
+
+
+def test_item_attention_impls_agree(engine):
+    """tcgen05 item attention against the warp-level mma.sync implementation (both bf16 in, fp32 accumulate)."""
+    g = torch.Generator().manual_seed(33)
+    N, F, M = 1500, 5, 700
+    Xc = torch.randn(N, F, generator=g)
+    yc = Xc[:, 1] + 0.1 * torch.randn(N, generator=g)
+    Xt = torch.randn(M, F, generator=g)
+    outs = []
+    for impl in (0, 1):
+        engine.set_option("attn_impl", impl)
+        engine.prefill(5, Xc, yc)
+        outs.append(engine.forward_logits(5, Xt))
+    engine.set_option("attn_impl", 1)
+    d = (outs[0] - outs[1]).abs()
+    print(f"mma vs tcgen05 item attention: max|dlogit|={d.max():.4f}")
+    assert d.max() <= LOGIT_ATOL
+
+
+# ---- reference-facing API (shapes / errors as in /root/reference/tests/test_npe_pfn.py) -------------------
+def test_api_sample_logprob_shapes_and_errors(engine):
+    from npe_pfn_b200 import BoxUniform, TabPFN_Based_NPE_PFN
+    theta, x, g = _toy(50, 2, 2, 1)
+    prior = torch.distributions.MultivariateNormal(torch.zeros(2), torch.eye(2))
+    for filt in ("standardized_euclidean_filtering", "latest_filtering", "random_filtering", "no_filtering"):
+        post = TabPFN_Based_NPE_PFN(prior=prior, filter_type=filt, filter_context_size=30,
+                                    regressor_init_kwargs={"engine": engine})
+        post.append_simulations(theta, x)
+        s = post.sample((30,), x[0])
+        assert s.shape == (30, 2) and s.device.type == "cpu" and torch.isfinite(s).all()
+        s2, lp2 = post.sample((10,), x[:1], with_log_prob=True)
+        assert s2.shape == (10, 2) and lp2.shape == (10,) and torch.isfinite(lp2).all()
+        lp = post.log_prob(s, x[0])
+        assert lp.shape == (30,) and torch.isfinite(lp).all()
+    with pytest.raises(ValueError):
+        post.sample((5,), x[:2])
+    with pytest.raises(ValueError):
+        post.log_prob(s, x[0], mode="nope")
+    with pytest.raises(ValueError):
+        TabPFN_Based_NPE_PFN(filter_type="unknown")
+    # box prior: real rejection, all draws inside the support, batch-size adaptation exercised
+    box = BoxUniform(-0.3 * torch.ones(2), 0.8 * torch.ones(2))
+    post = TabPFN_Based_NPE_PFN(prior=box, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    s = post.sample((500,), x[0], max_sampling_batch_size=200)
+    assert s.shape == (500, 2) and bool(box.support.check(s).all())
+    assert 0 < post.last_acceptance_rate <= 1
+    # elementwise-support prior (plain Uniform, as in the reference demo) takes the torch.all(dim=-1) branch
+    uni = torch.distributions.Uniform(-torch.ones(2), torch.ones(2))
+    post = TabPFN_Based_NPE_PFN(prior=uni, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    s = post.sample((64,), x[0])
+    assert s.shape == (64, 2) and bool(((s >= -1) & (s <= 1)).all())
+    # pickling drops the engine-backed model and rebuilds it
+    blob = pickle.dumps(NPE_PFN_CoreFactory(engine, theta, x))
+    post2 = pickle.loads(blob)
+    assert post2.sample((3,), x[0]).shape == (3, 2)
+
+
+def NPE_PFN_CoreFactory(engine, theta, x):
+    from npe_pfn_b200 import NPE_PFN_Core
+    prior = torch.distributions.MultivariateNormal(torch.zeros(2), torch.eye(2))
+    return NPE_PFN_Core(prior=prior).append_simulations(theta, x)
+
+
+def test_api_sample_batched(engine):
+    from npe_pfn_b200 import BoxUniform, NPE_PFN_Core
+    theta, x, g = _toy(60, 3, 2, 2)
+    post = NPE_PFN_Core(prior=None, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    s = post.sample_batched(x[:5], (20,))
+    assert s.shape == (5, 20, 2) and torch.isfinite(s).all()
+    s, lp = post.sample_batched(x[:3], (8,), with_log_prob=True)
+    assert s.shape == (3, 8, 2) and lp.shape == (3, 8)
+    box = BoxUniform(-2 * torch.ones(2), 2 * torch.ones(2))
+    post = NPE_PFN_Core(prior=box, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    s, lp = post.sample_batched(x[:4], (25,), with_log_prob=True)
+    assert s.shape == (4, 25, 2) and lp.shape == (4, 25) and bool(box.support.check(s.reshape(-1, 2)).all())
+    # a single observation through sample_batched has the shape of sample (test_npe_pfn.py:361-382)
+    assert post.sample_batched(x[:1], (10,)).shape == (1, 10, 2)
+    # the same observation repeated gives per-observation draws from the same distribution
+    s = post.sample_batched(x[:1].repeat(2, 1), (400,))
+    assert (s[0].mean(0) - s[1].mean(0)).abs().max() < 0.5
+
+
+def test_five_call_protocol(engine, weights):
+    """fit / predict / criterion.sample / criterion(logits, y), as npe_pfn.py:140-151 calls them."""
+    from npe_pfn_b200.estimator import B200TabPFNRegressor
+    theta, x, g = _toy(40, 2, 1, 4)
+    m = B200TabPFNRegressor(engine=engine, slot=6)
+    m.fit(x, theta[:, 0])
+    pd = m.predict(x[:9], output_type="full", quantiles=[])
+    assert set(pd) >= {"criterion", "logits"} and pd["logits"].shape == (9, weights.cfg.num_buckets)
+    torch.manual_seed(0)
+    a = pd["criterion"].sample(pd["logits"])
+    torch.manual_seed(0)
+    b = pd["criterion"].sample(pd["logits"])
+    assert a.shape == (9,) and a.device.type == "cpu" and torch.equal(a, b)
+    nll = pd["criterion"](pd["logits"], a)
+    assert nll.shape == (9,) and torch.isfinite(nll).all()
+
+
+def test_tsnpe_rounds_autoregressive(engine):
+    from npe_pfn_b200 import BoxUniform, run_tsnpe_pfn
+    torch.manual_seed(0)
+    prior = BoxUniform(-2 * torch.ones(2), 2 * torch.ones(2))
+
+    def simulator(theta):
+        return theta + 0.1 * torch.randn_like(theta)
+
+    post = run_tsnpe_pfn(simulator, prior, torch.zeros(1, 2), num_simulations=120, num_rounds=2,
+                         proposal_batch_size=200, simulation_batch_size=60, num_samples_to_estimate_support=200,
+                         allowed_false_negatives=0.01, log_prob_mode="autoregressive",
+                         regressor_init_kwargs={"engine": engine})
+    assert post._theta_train.shape == (120, 2)
+    s = post.sample((50,), torch.zeros(1, 2))
+    assert s.shape == (50, 2) and bool(prior.support.check(s).all())
