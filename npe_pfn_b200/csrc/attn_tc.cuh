@@ -1,0 +1,385 @@
+// Attention between items on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
+//
+// Same contract as attn_mma.cuh (AttnArgs): one CTA = 128 query vectors (dh = 32) of one (column t, head h)
+// against all N keys of that column.  Warp roles (192 threads):
+//   warps 0-3  softmax: thread i owns query row i = TMEM lane i.  Reads S from TMEM (tcgen05.ld), online
+//              softmax in fp32 registers with lazy rescaling, writes P (bf16) back into the S columns
+//              (tcgen05.st), so the second contraction takes P straight from TMEM.
+//   warp 4     TMA producer: Q tile once, then K/V tiles of 128 keys through a 5-stage mbarrier ring
+//              (cp.async.bulk.tensor, 64-byte swizzle = the canonical K-major / MN-major UMMA layouts).
+//   warp 5     TMEM allocation + single-thread MMA issue: S = Q K^T (M128 N128 K32, operands in shared
+//              memory) and O += P V (M128 N32 K128, A from TMEM, B = V tile MN-major); completion is
+//              signalled with tcgen05.commit on mbarriers.
+// Two CTAs are resident per SM (256 TMEM columns each), so one CTA's exponentials overlap the other's MMAs.
+#pragma once
+#include <cuda.h>
+
+#include "attn_mma.cuh"
+#include "common.cuh"
+
+namespace pfn {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 5, TC_THREADS = 192;
+constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 8 KB: 128 rows x 64 B
+constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // K tile + V tile
+constexpr int TC_SMEM_BYTES = 1024 + TC_TILE_BYTES + TC_STAGES * TC_STAGE_BYTES + 256;
+constexpr int TC_TMEM_COLS = 256;                     // S/P: [0,128), O: [128,160)
+constexpr int TC_COL_O = 128;
+
+struct TcArgs {
+    bf16* O;
+    int64_t o_row, o_tok;
+    int64_t R, N;
+    int kv_ctx_mode;  // 0: K/V map dims (64, N, T) box (32,128,1); 1: dims (ld, T, N) box (32,1,128)
+    int kx0, kx_head, v_dx;  // x coordinate of K for head 0, per-head step, V = K + v_dx
+};
+
+// ---- PTX wrappers ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]
+__device__ __forceinline__ void umma_ss(uint32_t d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(adesc), "l"(bdesc), "r"(idesc),
+        "r"(acc) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d), "r"(a), "l"(bdesc), "r"(idesc),
+        "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor, 64-byte swizzle, tile = rows of 64 bytes, 8-row groups 512 B apart
+// (cute::UMMA::SmemDescriptor: start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) | version=1 [46,48) | layout [61,64))
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;            // leading byte offset (unused for one swizzle atom in the leading dim)
+    d |= (uint64_t)(512 >> 4) << 32;   // stride byte offset: 8 rows x 64 B
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)4 << 61;            // SWIZZLE_64B
+    return d;
+}
+// instruction descriptor kind::f16: D fp32, A/B bf16 (cute::UMMA::InstrDescriptor)
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 2)
+attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs p) {
+    extern __shared__ uint8_t tc_smem_raw[];
+    const uint32_t raw = smem_u32(tc_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t sQ = base;
+    const uint32_t sKV = base + TC_TILE_BYTES;
+    const uint32_t bars = sKV + TC_STAGES * TC_STAGE_BYTES;
+    // barrier slots (8 B each)
+    const uint32_t bar_kv_full = bars;                     // [TC_STAGES]
+    const uint32_t bar_kv_empty = bars + 8 * TC_STAGES;    // [TC_STAGES]
+    const uint32_t bar_q = bars + 16 * TC_STAGES;
+    const uint32_t bar_s = bar_q + 8;
+    const uint32_t bar_p = bar_q + 16;
+    const uint32_t bar_o = bar_q + 24;
+    const uint32_t tmem_slot = bar_q + 32;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(tc_smem_raw + (tmem_slot - raw));
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int h = blockIdx.y, t = blockIdx.z;
+    const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
+    const int ntiles = (int)((p.N + TC_BN - 1) / TC_BN);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(bar_kv_full + 8 * s, 1);
+            mbar_init(bar_kv_empty + 8 * s, 1);
+        }
+        mbar_init(bar_q, 1);
+        mbar_init(bar_s, 1);
+        mbar_init(bar_p, 128);
+        mbar_init(bar_o, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 5) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)TC_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 4) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
+            mbar_expect_tx(bar_q, TC_TILE_BYTES);
+            tma_load_3d(sQ, &tmQ, bar_q, h * kDh, t, (int)m0);
+            const int kx = p.kx0 + h * p.kx_head;
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % TC_STAGES;
+                const uint32_t ph = (uint32_t)(j / TC_STAGES) & 1u;
+                mbar_wait(bar_kv_empty + 8 * s, ph ^ 1u);
+                mbar_expect_tx(bar_kv_full + 8 * s, TC_STAGE_BYTES);
+                const uint32_t dstK = sKV + s * TC_STAGE_BYTES, dstV = dstK + TC_TILE_BYTES;
+                const int key0 = j * TC_BN;
+                if (p.kv_ctx_mode) {
+                    tma_load_3d(dstK, &tmKV, bar_kv_full + 8 * s, kx, t, key0);
+                    tma_load_3d(dstV, &tmKV, bar_kv_full + 8 * s, kx + p.v_dx, t, key0);
+                } else {
+                    tma_load_3d(dstK, &tmKV, bar_kv_full + 8 * s, kx, key0, t);
+                    tma_load_3d(dstV, &tmKV, bar_kv_full + 8 * s, kx + p.v_dx, key0, t);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        // ================= MMA issuer =================
+        constexpr uint32_t idesc_qk = umma_idesc_bf16(TC_BM, TC_BN, 0, 0);
+        constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, kDh, 0, 1);
+        const uint64_t descQ = umma_desc_sw64(sQ);
+        auto issue_qk = [&](int s) {
+            const uint64_t descK = umma_desc_sw64(sKV + s * TC_STAGE_BYTES);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)  // dh = 32 = 2 x K16; 32 bytes per step inside the swizzle atom
+                umma_ss(tmem, descQ + (uint64_t)(kk * 2), descK + (uint64_t)(kk * 2), idesc_qk, kk > 0);
+        };
+        mbar_wait(bar_q, 0);
+        mbar_wait(bar_kv_full, 0);
+        tc_fence_after();
+        if (lane == 0) {
+            issue_qk(0);
+            tc_commit(bar_s);
+        }
+        __syncwarp();
+        for (int j = 0; j < ntiles; ++j) {
+            const int s = j % TC_STAGES;
+            mbar_wait(bar_p, (uint32_t)j & 1u);
+            tc_fence_after();
+            if (lane == 0) {
+                const uint64_t descV = umma_desc_sw64(sKV + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+#pragma unroll
+                for (int kk = 0; kk < TC_BN / 16; ++kk)  // 16 keys per step: 8 TMEM columns of P, 1 KB of V
+                    umma_ts(tmem + TC_COL_O, tmem + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
+                tc_commit(bar_kv_empty + 8 * s);
+            }
+            __syncwarp();
+            if (j + 1 < ntiles) {
+                const int s1 = (j + 1) % TC_STAGES;
+                mbar_wait(bar_kv_full + 8 * s1, (uint32_t)((j + 1) / TC_STAGES) & 1u);
+                tc_fence_after();
+                if (lane == 0) {
+                    issue_qk(s1);
+                    tc_commit(bar_s);
+                }
+            } else if (lane == 0) {
+                tc_commit(bar_o);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ================= softmax warps: thread = query row = TMEM lane =================
+        const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+        float m_ref = -INFINITY, l = 0.f;
+        uint32_t sv[4][32];
+        for (int j = 0; j < ntiles; ++j) {
+            mbar_wait(bar_s, (uint32_t)j & 1u);
+            tc_fence_after();
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tmem_ld32(trow + c * 32, sv[c]);
+            tmem_wait_ld();
+            const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
+            if (nvalid < TC_BN) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (c * 32 + i >= nvalid) sv[c][i] = 0xff800000u;  // -inf
+            }
+            float mx = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
+            const float mt = mx * sc;
+            if (j == 0) {
+                m_ref = mt;
+            } else {
+                // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
+                const bool need = mt > m_ref + 8.0f;
+                if (__any_sync(0xffffffffu, need)) {
+                    const float corr = need ? fast_exp2(m_ref - mt) : 1.0f;
+                    if (need) m_ref = mt;
+                    l *= corr;
+                    uint32_t ov[32];
+                    tmem_ld32(trow + TC_COL_O, ov);
+                    tmem_wait_ld();
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                    tmem_st32(trow + TC_COL_O, ov);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                uint32_t pk[32];
+#pragma unroll
+                for (int i = 0; i < 32; ++i) {
+                    const int cc = 2 * c + (i >> 4), ii = (2 * i) & 31;
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii]), sc, -m_ref));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii + 1]), sc, -m_ref));
+                    l += p0 + p1;
+                    pk[i] = pack_bf16x2(p0, p1);
+                }
+                tmem_st32(trow + c * 32, pk);
+            }
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar_p);
+        }
+        // ---- epilogue: O / l -> bf16 -> global ----
+        mbar_wait(bar_o, 0);
+        tc_fence_after();
+        uint32_t ov[32];
+        tmem_ld32(trow + TC_COL_O, ov);
+        tmem_wait_ld();
+        const int64_t r = m0 + warp * 32 + lane;
+        if (r < p.R) {
+            const float inv = 1.0f / l;
+            uint4* dst = reinterpret_cast<uint4*>(p.O + r * p.o_row + (int64_t)t * p.o_tok + h * kDh);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint4 v;
+                v.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
+                v.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
+                v.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
+                v.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
+                dst[q] = v;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// ---- host side: tensor maps + launch ---------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                    const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                    CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static inline PFN_encodeTiled get_encode_fn() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<PFN_encodeTiled>(ptr);
+    }
+    return fn;
+}
+
+// 3-D bf16 map; dims/box innermost first; strides (bytes) of dims 1 and 2
+static inline bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint64_t d1, uint64_t d2, uint64_t s1,
+                             uint64_t s2, uint32_t b0, uint32_t b1, uint32_t b2) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[3] = {d0, d1, d2};
+    cuuint64_t strides[2] = {s1, s2};
+    cuuint32_t box[3] = {b0, b1, b2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap mq, mkv;
+    TcArgs p{};
+    p.O = a.O; p.o_row = a.o_row; p.o_tok = a.o_tok; p.R = a.R; p.N = a.N;
+    // queries: element (x, t, r) at Q + r*q_row + t*q_tok + x
+    if (!make_map3(&mq, a.Q, (uint64_t)a.q_tok, (uint64_t)T, (uint64_t)a.R, (uint64_t)a.q_tok * 2, (uint64_t)a.q_row * 2,
+                   kDh, 1, TC_BM))
+        return cudaErrorInvalidValue;
+    if (a.k_head) {
+        // context rows: keys live in the projected qkv buffer, element (x, t, j) at base + j*k_row + t*k_tok + x
+        const bf16* basep = a.K - kE;  // a.K points at the K block (column kE) of the qkv rows
+        if (!make_map3(&mkv, basep, (uint64_t)a.k_tok, (uint64_t)T, (uint64_t)a.N, (uint64_t)a.k_tok * 2,
+                       (uint64_t)a.k_row * 2, kDh, 1, TC_BN))
+            return cudaErrorInvalidValue;
+        p.kv_ctx_mode = 1; p.kx0 = kE; p.kx_head = a.k_head; p.v_dx = a.v_off;
+    } else {
+        // cached head-0 K/V: element (x, j, t) at base + t*k_tok + j*k_row + x, rows of 64 (K | V)
+        if (!make_map3(&mkv, a.K, (uint64_t)kKvRow, (uint64_t)a.N, (uint64_t)T, (uint64_t)a.k_row * 2,
+                       (uint64_t)a.k_tok * 2, kDh, TC_BN, 1))
+            return cudaErrorInvalidValue;
+        p.kv_ctx_mode = 0; p.kx0 = 0; p.kx_head = 0; p.v_dx = a.v_off;
+    }
+    dim3 grid((unsigned)ceil_div(a.R, TC_BM), (unsigned)heads, (unsigned)T);
+    attn_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
+    return cudaGetLastError();
+}
+
+}  // namespace pfn

@@ -165,7 +165,11 @@ def test_fused_sampling_vs_reference_loop(engine, weights):
     print("|dtheta| / posterior std: median", dth.median(0).values.tolist(), "max", dth.max(0).values.tolist())
     assert dth[:, 0].median() <= 0.05 and dth.median() <= 0.1
     assert (s.mean(0) - s_ref.mean(0)).abs().max() <= 0.1 * spread.max()
-    assert (lp - lp_ref).abs().median() < 3 * LOGP_ATOL
+    # log-density of a draw is only comparable where both paths landed in the same buckets (the random-init
+    # density differs by e^2.6 between neighbouring buckets)
+    same = (bins.cpu() == bins_ref).all(1)
+    assert same.any()
+    assert (lp - lp_ref).abs()[same].max() <= 3 * LOGP_ATOL
 
 
 def test_log_prob_vs_reference_loop(engine, weights):
