@@ -1,15 +1,20 @@
-"""TSNPE truncated proposal and context filters — same behaviour as
-`/root/reference/npe_pfn/support_posterior.py` (PosteriorSupport :13-258, prereject_with_bounds :264-309,
-filters :327-369), running over the B200 posterior object.
+"""TSNPE truncated proposal ("posterior support") and the context filters, over the B200 posterior object.
 
-threshold = eps-quantile of the posterior log-prob over posterior samples (:61-69); a prior draw is kept when
-its posterior log-prob exceeds it (:133-160); on `max_iter` exhaustion the rest is topped up with raw prior
-draws (:171-174).
+Behavioural contract (what `/root/reference/npe_pfn/support_posterior.py` does):
+  * `PosteriorSupport(prior, posterior, obs, ...)`: draw `num_samples_to_estimate_support` posterior samples, set
+    `thr` = the `allowed_false_negatives`-quantile of their posterior log-prob (:42-52, :61-69);
+  * `.sample((n,))`, rejection mode: propose from the prior (narrowed to the classifier's box when the posterior
+    exposes one, :137-152), keep proposals whose posterior log-prob exceeds `thr`, at most `max_iter_rejection`
+    rounds of `sampling_batch_size` proposals, then top up with raw prior draws (:133-174);
+  * SIR mode (:184-258): groups of `oversample_sir` posterior draws, one survivor per group drawn with weights
+    prior/posterior (draws under the adaptive log-prob quantile get weight zero);
+  * context filters (:327-369) return `(theta, x)`; the default keeps the `context_size` simulations nearest to the
+    observation in z-scored x, ordered by distance.
 """
 from __future__ import annotations
 
 import logging
-from typing import Any, Mapping
+from typing import Any, Callable, Dict, Mapping, Optional, Tuple
 
 import torch
 from torch import Tensor
@@ -35,196 +40,183 @@ class PosteriorSupport:
         oversample_sir: int = 100,
         log_prob_kwargs: Mapping = {},
     ) -> None:
-        self._prior = prior
-        self._posterior = posterior
-        self._obs = obs
+        self._prior, self._posterior, self._obs = prior, posterior, obs
+        self._log_prob_kwargs = dict(log_prob_kwargs)
         self._posterior_thr = None
         self.sampling_method = sampling_method
         self.max_iter = max_iter_rejection
         self.oversample_sir = oversample_sir
         self.allowed_false_negatives = allowed_false_negatives
-        self._log_prob_kwargs = log_prob_kwargs
-
         if sampling_method == "rejection":
-            samples_to_estimate_support = self._posterior.sample(
-                (num_samples_to_estimate_support,), self._obs,
-                max_sampling_batch_size=batch_size_for_estimate_support)
-            self.thr = self.tune_threshold(samples_to_estimate_support, allowed_false_negatives,
-                                           batch_size=batch_size_for_estimate_support)
+            # the same posterior draws serve for the quantile and (implicitly) for the support estimate
+            draws = posterior.sample((num_samples_to_estimate_support,), obs,
+                                     max_sampling_batch_size=batch_size_for_estimate_support)
+            self.thr = self.tune_threshold(draws, allowed_false_negatives, batch_size=batch_size_for_estimate_support)
+
+    # -- threshold ------------------------------------------------------------------------------------------
+    def _posterior_log_prob(self, theta: Tensor, **extra) -> Tensor:
+        return self._posterior.log_prob(theta, self._obs, **extra, **self._log_prob_kwargs)
 
     def tune_threshold(self, samples: Tensor, allowed_false_negatives: float = 0.0, batch_size: int = 10_000):
-        log_probs = self._posterior.log_prob(samples, self._obs, max_sampling_batch_size=batch_size,
-                                             **self._log_prob_kwargs)
-        return torch.quantile(log_probs, allowed_false_negatives)
+        return torch.quantile(self._posterior_log_prob(samples, max_sampling_batch_size=batch_size),
+                              allowed_false_negatives)
 
+    # -- dispatch -------------------------------------------------------------------------------------------
     def sample(self, sample_shape: torch.Size = torch.Size(), show_progress_bars: bool = True,
                sampling_batch_size: int = 10_000, return_acceptance_rate: bool = False, return_ess: bool = False):
+        common = dict(sample_shape=sample_shape, show_progress_bars=show_progress_bars,
+                      sampling_batch_size=sampling_batch_size)
         if self.sampling_method == "rejection":
-            return self.sample_rejection(sample_shape=sample_shape, show_progress_bars=show_progress_bars,
-                                         sampling_batch_size=sampling_batch_size,
-                                         return_acceptance_rate=return_acceptance_rate)
-        elif self.sampling_method == "sir":
-            return self.sample_sir(sample_shape=sample_shape, show_progress_bars=show_progress_bars,
-                                   sampling_batch_size=sampling_batch_size, return_ess=return_ess)
+            return self.sample_rejection(return_acceptance_rate=return_acceptance_rate, **common)
+        if self.sampling_method == "sir":
+            return self.sample_sir(return_ess=return_ess, **common)
         raise ValueError(f"Unknown sampling method: {self.sampling_method}")
+
+    # -- rejection ------------------------------------------------------------------------------------------
+    def _proposal_round(self, box: Tuple[Optional[Tensor], Optional[Tensor]], n: int):
+        """One batch of prior proposals and their posterior log-prob.  Returns (candidates, log_probs, box,
+        pre-acceptance rate); `box` is the classifier's padded bounding box once the posterior has one."""
+        lo, hi = box
+        if lo is None or hi is None:
+            cand, pre_rate = self._prior.sample((n,)), None
+        else:
+            cand, pre_rate = prereject_with_bounds(self._prior, lo, hi, n)
+        lp = self._posterior_log_prob(cand)
+        new_lo, new_hi = self._posterior._get_classifier_bounds()
+        if lo is not None and hi is not None:  # the box must not move between rounds
+            assert torch.allclose(lo, new_lo) and torch.allclose(hi, new_hi)
+        return cand, lp, (new_lo, new_hi), pre_rate
 
     def sample_rejection(self, sample_shape: torch.Size = torch.Size(), show_progress_bars: bool = True,
                          sampling_batch_size: int = 10_000, return_acceptance_rate: bool = False):
-        assert len(sample_size := torch.Size(sample_shape)) == 1
-        num_samples = sample_size[0]
-        pbar = tqdm(disable=not show_progress_bars, total=num_samples,
-                    desc=f"Drawing {num_samples} restricted posterior samples")
-        pre_acceptance_rate = 1.0
-        lower, upper = None, None
-        num_sampled_total, num_remaining = 0, num_samples
-        accepted = []
-        for _ in range(self.max_iter):
-            if num_remaining <= 0:
-                break
-            if lower is None or upper is None:
-                candidates = self._prior.sample((sampling_batch_size,))
-                log_probs = self._posterior.log_prob(candidates, self._obs, **self._log_prob_kwargs)
-                lower, upper = self._posterior._get_classifier_bounds()
-            else:
-                candidates, pre_acceptance_rate = prereject_with_bounds(self._prior, lower, upper, sampling_batch_size)
-                log_probs = self._posterior.log_prob(candidates, self._obs, **self._log_prob_kwargs)
-                sanity_lower, sanity_upper = self._posterior._get_classifier_bounds()
-                assert torch.allclose(lower, sanity_lower)
-                assert torch.allclose(upper, sanity_upper)
-            are_accepted = log_probs > self.thr
-            samples = candidates[are_accepted.bool()]
-            accepted.append(samples)
-            num_sampled_total += sampling_batch_size
-            num_remaining -= samples.shape[0]
-            pbar.update(samples.shape[0])
-        pbar.close()
+        shape = torch.Size(sample_shape)
+        assert len(shape) == 1, "only 1-D sample shapes are supported"
+        wanted = shape[0]
+        bar = tqdm(disable=not show_progress_bars, total=wanted, desc=f"Drawing {wanted} restricted posterior samples")
+        kept, n_kept, n_proposed = [], 0, 0
+        box: Tuple[Optional[Tensor], Optional[Tensor]] = (None, None)
+        pre_rate = 1.0
+        rounds = 0
+        while n_kept < wanted and rounds < self.max_iter:
+            cand, lp, box, r = self._proposal_round(box, sampling_batch_size)
+            if r is not None:
+                pre_rate = r
+            good = cand[(lp > self.thr).bool()]
+            kept.append(good)
+            n_kept += good.shape[0]
+            n_proposed += sampling_batch_size
+            rounds += 1
+            bar.update(good.shape[0])
+        bar.close()
+        lp_rate = n_kept / max(n_proposed, 1)
+        overall = pre_rate * lp_rate
+        log.info("pre-acceptance %.4g, log-prob acceptance %.4g, overall %.4g", pre_rate, lp_rate, overall)
+        if n_kept < wanted:  # iteration budget exhausted: fill with unrestricted prior draws
+            missing = wanted - n_kept
+            kept.append(self._prior.sample((missing,)))
+            log.info("max_iter reached: added %d raw prior samples", missing)
+        out = torch.cat(kept)[:wanted]
+        assert out.shape[0] == wanted
+        return (out, overall) if return_acceptance_rate else out
 
-        acceptance_rate = (num_samples - num_remaining) / max(num_sampled_total, 1)
-        log.info(f"Pre-acceptance rate: {pre_acceptance_rate}")
-        log.info(f"Log prob acceptance rate: {acceptance_rate}")
-        overall_acceptance_rate = pre_acceptance_rate * acceptance_rate
-        log.info(f"Overall acceptance rate: {overall_acceptance_rate}")
-        if num_remaining > 0:
-            remaining_samples = self._prior.sample((num_remaining,))
-            accepted.append(remaining_samples)
-            log.info(f"Max iter exceeded. Added {num_remaining} prior samples.")
-        samples = torch.cat(accepted)[:num_samples]
-        assert samples.shape[0] == num_samples
-        if return_acceptance_rate:
-            return samples, overall_acceptance_rate
-        return samples
-
+    # -- sampling importance resampling --------------------------------------------------------------------------
     def sample_sir(self, sample_shape: torch.Size = torch.Size(), show_progress_bars: bool = True,
                    sampling_batch_size: int = 10_000, return_ess: bool = False):
-        """Sampling-importance-resampling variant (support_posterior.py:184-258)."""
-        assert len(sample_size := torch.Size(sample_shape)) == 1
-        num_samples = sample_size[0]
-        pbar = tqdm(disable=not show_progress_bars, total=num_samples,
-                    desc=f"Drawing {num_samples} restricted posterior samples")
-        oversampling_factor = self.oversample_sir
-        assert sampling_batch_size % oversampling_factor == 0
-        sir_batch_size = sampling_batch_size // oversampling_factor
-        num_remaining = num_samples
-        all_samples, all_ess = [], []
-        while num_remaining > 0:
-            posterior_samples, posterior_log_probs = self._posterior.sample(
-                (sampling_batch_size,), self._obs, max_sampling_batch_size=sampling_batch_size, with_log_prob=True)
-            truncated_prior_log_probs = self._prior.log_prob(posterior_samples)
-            thr = torch.quantile(posterior_log_probs, self.allowed_false_negatives)
-            truncated_prior_log_probs[posterior_log_probs < thr] = -float("inf")
-            log_ratios = torch.nan_to_num(truncated_prior_log_probs - posterior_log_probs, -float("inf"))
-            reshaped_ratio = torch.reshape(log_ratios, (sir_batch_size, oversampling_factor))
-            probs = torch.exp(reshaped_ratio - torch.logsumexp(reshaped_ratio, dim=1, keepdim=True))
-            all_ess.append(1.0 / torch.sum(probs**2, dim=1))
-            cat_dist = torch.distributions.Categorical(logits=reshaped_ratio)
-            categorical_samples = cat_dist.sample((1,))[0, :]
-            reshaped_posterior_samples = torch.reshape(posterior_samples, (sir_batch_size, self.oversample_sir, -1))
-            all_samples.append(reshaped_posterior_samples[torch.arange(sir_batch_size), categorical_samples])
-            num_remaining -= sir_batch_size
-            pbar.update(sir_batch_size)
-        pbar.close()
-        samples = torch.cat(all_samples)[:num_samples]
-        assert samples.shape[0] == num_samples
-        ess = torch.cat(all_ess)
-        log.info(f"Mean ESS: {ess.mean().item()}")
-        log.info(f"Min ESS: {ess.min().item()}")
-        if return_ess:
-            return samples, ess
-        return samples
+        shape = torch.Size(sample_shape)
+        assert len(shape) == 1, "only 1-D sample shapes are supported"
+        wanted = shape[0]
+        k = self.oversample_sir
+        assert sampling_batch_size % k == 0, "sampling_batch_size must be a multiple of oversample_sir"
+        groups = sampling_batch_size // k
+        bar = tqdm(disable=not show_progress_bars, total=wanted, desc=f"Drawing {wanted} restricted posterior samples")
+        chosen, ess_parts, have = [], [], 0
+        while have < wanted:
+            theta, lp_post = self._posterior.sample((sampling_batch_size,), self._obs,
+                                                    max_sampling_batch_size=sampling_batch_size, with_log_prob=True)
+            lp_prior = self._prior.log_prob(theta)
+            cut = torch.quantile(lp_post, self.allowed_false_negatives)  # adaptive threshold per batch
+            lp_prior = torch.where(lp_post < cut, torch.full_like(lp_prior, -float("inf")), lp_prior)
+            logw = torch.nan_to_num(lp_prior - lp_post, -float("inf")).reshape(groups, k)
+            w = torch.softmax(logw, dim=1)
+            ess_parts.append(1.0 / (w * w).sum(dim=1))
+            pick = torch.distributions.Categorical(logits=logw).sample()
+            chosen.append(theta.reshape(groups, k, -1)[torch.arange(groups), pick])
+            have += groups
+            bar.update(groups)
+        bar.close()
+        out = torch.cat(chosen)[:wanted]
+        assert out.shape[0] == wanted
+        ess = torch.cat(ess_parts)
+        log.info("ESS mean %.3f min %.3f", ess.mean().item(), ess.min().item())
+        return (out, ess) if return_ess else out
+
+
+# ---- box pre-rejection ------------------------------------------------------------------------------------------
+def check_for_uniform(proposal: Any) -> bool:
+    return isinstance(proposal, BoxUniform) or (isinstance(proposal, Independent)
+                                                and isinstance(proposal.base_dist, Uniform))
+
+
+def get_uniform_bounds(proposal) -> Tuple[Tensor, Tensor]:
+    return proposal.base_dist.low, proposal.base_dist.high
 
 
 def prereject_with_bounds(proposal: Any, lower_bound: Tensor, upper_bound: Tensor, sampling_batch_size: int = 10_000,
                           pre_sampling_batch_size: int = 1_000_000):
-    """Pre-reject proposal draws outside [lower, upper] (support_posterior.py:264-309)."""
-    is_uniform = check_for_uniform(proposal)
-    num_pre_accepted = 0
-    num_sampled_total = 0
-    pre_samples = []
-    while num_pre_accepted < sampling_batch_size:
-        samples = proposal.sample((pre_sampling_batch_size,))
-        within_bounds = torch.all((samples >= lower_bound) & (samples <= upper_bound), dim=1)
-        samples = samples[within_bounds.bool()]
-        pre_samples.append(samples)
-        num_pre_accepted += samples.shape[0]
-        num_sampled_total += pre_sampling_batch_size
-        if is_uniform:
+    """`sampling_batch_size` proposal draws inside [lower, upper] and the fraction of raw draws that fell inside.
+
+    A uniform proposal is intersected with the box analytically (one raw batch only estimates the rate);
+    anything else is filtered batch by batch until enough draws survive (support_posterior.py:264-309)."""
+    uniform = check_for_uniform(proposal)
+    inside, n_inside, n_raw = [], 0, 0
+    while True:
+        raw = proposal.sample((pre_sampling_batch_size,))
+        ok = ((raw >= lower_bound) & (raw <= upper_bound)).all(dim=1)
+        inside.append(raw[ok])
+        n_inside += int(ok.sum())
+        n_raw += pre_sampling_batch_size
+        if uniform or n_inside >= sampling_batch_size:
             break
-    pre_acceptance_rate = num_pre_accepted / num_sampled_total
-    if is_uniform:
-        prop_lower_bound, prop_upper_bound = get_uniform_bounds(proposal)
-        max_lower = torch.max(lower_bound, prop_lower_bound)
-        min_upper = torch.min(upper_bound, prop_upper_bound)
-        return BoxUniform(max_lower, min_upper).sample((sampling_batch_size,)), pre_acceptance_rate
-    return torch.cat(pre_samples)[:sampling_batch_size], pre_acceptance_rate
+    rate = n_inside / n_raw
+    if uniform:
+        p_lo, p_hi = get_uniform_bounds(proposal)
+        return BoxUniform(torch.max(lower_bound, p_lo), torch.min(upper_bound, p_hi)).sample((sampling_batch_size,)), rate
+    return torch.cat(inside)[:sampling_batch_size], rate
 
 
-def check_for_uniform(proposal: Any):
-    if isinstance(proposal, BoxUniform):
-        return True
-    if isinstance(proposal, Independent) and isinstance(proposal.base_dist, Uniform):
-        return True
-    return False
-
-
-def get_uniform_bounds(proposal):
-    return proposal.base_dist.low, proposal.base_dist.high
-
-
-# filter functions always return (theta, x) in that order (support_posterior.py:326)
-def get_filtering_method(name):
-    if name == "no_filtering":
-        return no_filtering
-    elif name == "latest_filtering":
-        return latest_filtering
-    elif name == "random_filtering":
-        return random_filtering
-    elif name == "standardized_euclidean_filtering":
-        return standardized_euclidean_filtering
-    elif callable(name):
-        return name
-    raise ValueError(f"Unknown filtering method: {name}")
-
-
+# ---- context filters: (obs, theta, x, context_size) -> (theta, x) -------------------------------------------------
 def no_filtering(obs: Tensor, theta: Tensor, x: Tensor, context_size: int):
     return theta, x
 
 
 def latest_filtering(obs: Tensor, theta: Tensor, x: Tensor, context_size: int):
+    """the newest simulations are at the end"""
     return theta[-context_size:], x[-context_size:]
 
 
 def random_filtering(obs: Tensor, theta: Tensor, x: Tensor, context_size: int):
-    perm = torch.randperm(theta.shape[0])
-    return theta[perm[:context_size]], x[perm[:context_size]]
+    keep = torch.randperm(theta.shape[0])[:context_size]
+    return theta[keep], x[keep]
 
 
 def standardized_euclidean_filtering(obs: Tensor, theta: Tensor, x: Tensor, context_size: int):
-    """z-score x, L2 distance to the observation, keep the `context_size` nearest, ordered by distance
-    (support_posterior.py:357-369)."""
-    x_mean = x.mean(dim=0)
-    x_std = x.std(dim=0)
-    x_s = (x - x_mean) / x_std
-    obs_s = (obs - x_mean) / x_std
-    dists = torch.norm(x_s - obs_s, dim=1)
-    _, idx = torch.topk(dists, min(context_size, dists.shape[0]), largest=False)
-    return theta[idx], x[idx]
+    mu, sd = x.mean(dim=0), x.std(dim=0)
+    dist = torch.norm((x - mu) / sd - (obs - mu) / sd, dim=1)
+    nearest = torch.topk(dist, min(context_size, dist.shape[0]), largest=False).indices
+    return theta[nearest], x[nearest]
+
+
+_FILTERS: Dict[str, Callable] = {
+    "no_filtering": no_filtering,
+    "latest_filtering": latest_filtering,
+    "random_filtering": random_filtering,
+    "standardized_euclidean_filtering": standardized_euclidean_filtering,
+}
+
+
+def get_filtering_method(name):
+    if isinstance(name, str) and name in _FILTERS:
+        return _FILTERS[name]
+    if callable(name):
+        return name
+    raise ValueError(f"Unknown filtering method: {name}")
