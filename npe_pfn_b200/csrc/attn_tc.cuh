@@ -1,16 +1,19 @@
 // Attention between items on the 5th-generation tensor cores (tcgen05 + TMEM + TMA), sm_100a only.
 //
 // Same contract as attn_mma.cuh (AttnArgs): one CTA = 128 query vectors (dh = 32) of one (column t, head h)
-// against all N keys of that column.  Warp roles (192 threads):
+// against all N keys of that column, streamed in tiles of 64 keys.  Warp roles (192 threads):
 //   warps 0-3  softmax: thread i owns query row i = TMEM lane i.  Reads S from TMEM (tcgen05.ld), online
 //              softmax in fp32 registers with lazy rescaling, writes P (bf16) back into the S columns
 //              (tcgen05.st), so the second contraction takes P straight from TMEM.
-//   warp 4     TMA producer: Q tile once, then K/V tiles of 128 keys through a 5-stage mbarrier ring
+//   warp 4     TMA producer: Q tile once, then K/V tiles through an 8-stage mbarrier ring
 //              (cp.async.bulk.tensor, 64-byte swizzle = the canonical K-major / MN-major UMMA layouts).
-//   warp 5     TMEM allocation + single-thread MMA issue: S = Q K^T (M128 N128 K32, operands in shared
-//              memory) and O += P V (M128 N32 K128, A from TMEM, B = V tile MN-major); completion is
+//   warp 5     TMEM allocation + single-thread MMA issue: S_j = Q K_j^T (M128 N64 K32, operands in shared
+//              memory) and O += P_j V_j (M128 N32 K64, A from TMEM, B = V tile MN-major); completion is
 //              signalled with tcgen05.commit on mbarriers.
-// Two CTAs are resident per SM (256 TMEM columns each), so one CTA's exponentials overlap the other's MMAs.
+// S is double-buffered in TMEM and the MMA thread runs one tile ahead (QK_{j+1} is issued before the softmax of
+// tile j finishes), so the exponential pipe (MUFU, the real bound at dh = 32: 128 FLOP per ex2) never waits
+// for the tensor pipe.  Two CTAs are resident per SM (256 TMEM columns each).
+// r1 profile of the first version (single S buffer, 128-key tiles): profiles/r1_ncu_attn_tc_v1_metrics.txt.
 #pragma once
 #include <cuda.h>
 
@@ -19,18 +22,19 @@
 
 namespace pfn {
 
-constexpr int TC_BM = 128, TC_BN = 128, TC_STAGES = 5, TC_THREADS = 192;
-constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 8 KB: 128 rows x 64 B
+constexpr int TC_BM = 128, TC_BN = 64, TC_STAGES = 8, TC_THREADS = 192;
+constexpr int TC_Q_BYTES = TC_BM * kDh * 2;           // 8 KB: 128 rows x 64 B
+constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 4 KB: 64 keys x 64 B
 constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // K tile + V tile
-constexpr int TC_SMEM_BYTES = 1024 + TC_TILE_BYTES + TC_STAGES * TC_STAGE_BYTES + 256;
-constexpr int TC_TMEM_COLS = 256;                     // S/P: [0,128), O: [128,160)
+constexpr int TC_SMEM_BYTES = 1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256 + 16 * 1024;  // pad: 2 CTAs / SM
+constexpr int TC_TMEM_COLS = 256;                     // S0/P0: [0,64), S1/P1: [64,128), O: [128,160)
 constexpr int TC_COL_O = 128;
 
 struct TcArgs {
     bf16* O;
     int64_t o_row, o_tok;
     int64_t R, N;
-    int kv_ctx_mode;  // 0: K/V map dims (64, N, T) box (32,128,1); 1: dims (ld, T, N) box (32,1,128)
+    int kv_ctx_mode;  // 0: K/V map dims (64, N, T) box (32,64,1); 1: dims (ld, T, N) box (32,1,64)
     int kx0, kx_head, v_dx;  // x coordinate of K for head 0, per-head step, V = K + v_dx
 };
 
@@ -123,16 +127,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t sQ = base;
-    const uint32_t sKV = base + TC_TILE_BYTES;
+    const uint32_t sKV = base + TC_Q_BYTES;
     const uint32_t bars = sKV + TC_STAGES * TC_STAGE_BYTES;
     // barrier slots (8 B each)
-    const uint32_t bar_kv_full = bars;                     // [TC_STAGES]
-    const uint32_t bar_kv_empty = bars + 8 * TC_STAGES;    // [TC_STAGES]
-    const uint32_t bar_q = bars + 16 * TC_STAGES;
-    const uint32_t bar_s = bar_q + 8;
-    const uint32_t bar_p = bar_q + 16;
-    const uint32_t bar_o = bar_q + 24;
-    const uint32_t tmem_slot = bar_q + 32;
+    const uint32_t bar_kv_full = bars;                     // [TC_STAGES]  TMA -> MMA
+    const uint32_t bar_kv_empty = bars + 8 * TC_STAGES;    // [TC_STAGES]  MMA -> TMA
+    const uint32_t bar_q = bars + 16 * TC_STAGES;          // Q tile landed
+    const uint32_t bar_s = bar_q + 8;                      // [2] S buffer b holds Q K_j^T          MMA -> softmax
+    const uint32_t bar_p = bar_q + 24;                     // [2] P_j written into S buffer b       softmax -> MMA
+    const uint32_t bar_pv = bar_q + 40;                    // O += P_j V_j finished (rescale guard) MMA -> softmax
+    const uint32_t bar_o = bar_q + 48;                     // last O += P V finished
+    const uint32_t tmem_slot = bar_q + 56;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(tc_smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -147,7 +152,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         }
         mbar_init(bar_q, 1);
         mbar_init(bar_s, 1);
+        mbar_init(bar_s + 8, 1);
         mbar_init(bar_p, 128);
+        mbar_init(bar_p + 8, 128);
+        mbar_init(bar_pv, 1);
         mbar_init(bar_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -166,7 +174,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
-            mbar_expect_tx(bar_q, TC_TILE_BYTES);
+            mbar_expect_tx(bar_q, TC_Q_BYTES);
             tma_load_3d(sQ, &tmQ, bar_q, h * kDh, t, (int)m0);
             const int kx = p.kx0 + h * p.kx_head;
             for (int j = 0; j < ntiles; ++j) {
@@ -186,75 +194,72 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             }
         }
     } else if (warp == 5) {
-        // ================= MMA issuer =================
-        constexpr uint32_t idesc_qk = umma_idesc_bf16(TC_BM, TC_BN, 0, 0);
-        constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, kDh, 0, 1);
-        const uint64_t descQ = umma_desc_sw64(sQ);
-        auto issue_qk = [&](int s) {
-            const uint64_t descK = umma_desc_sw64(sKV + s * TC_STAGE_BYTES);
-#pragma unroll
-            for (int kk = 0; kk < 2; ++kk)  // dh = 32 = 2 x K16; 32 bytes per step inside the swizzle atom
-                umma_ss(tmem, descQ + (uint64_t)(kk * 2), descK + (uint64_t)(kk * 2), idesc_qk, kk > 0);
-        };
-        mbar_wait(bar_q, 0);
-        mbar_wait(bar_kv_full, 0);
-        tc_fence_after();
+        // ================= MMA issuer (one thread) =================
+        // Issue order: QK_0, QK_1, then per tile j: [wait P_j] PV_j, QK_{j+2}.  tcgen05.mma executes in issue
+        // order, so QK_{j+2} (which overwrites S buffer j%2 = P_j) cannot pass PV_j, and the softmax warps always
+        // find S_{j+1} ready when they finish tile j.
         if (lane == 0) {
+            constexpr uint32_t idesc_qk = umma_idesc_bf16(TC_BM, TC_BN, 0, 0);
+            constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, kDh, 0, 1);
+            const uint64_t descQ = umma_desc_sw64(sQ);
+            auto issue_qk = [&](int j) {
+                const int s = j % TC_STAGES;
+                mbar_wait(bar_kv_full + 8 * s, (uint32_t)(j / TC_STAGES) & 1u);
+                tc_fence_after();
+                const uint64_t descK = umma_desc_sw64(sKV + s * TC_STAGE_BYTES);
+                const uint32_t d = tmem + (uint32_t)((j & 1) * TC_BN);
+#pragma unroll
+                for (int kk = 0; kk < 2; ++kk)  // dh = 32 = 2 x K16; 32 bytes per step inside the swizzle atom
+                    umma_ss(d, descQ + (uint64_t)(kk * 2), descK + (uint64_t)(kk * 2), idesc_qk, kk > 0);
+                tc_commit(bar_s + 8 * (j & 1));
+            };
+            mbar_wait(bar_q, 0);
             issue_qk(0);
-            tc_commit(bar_s);
-        }
-        __syncwarp();
-        for (int j = 0; j < ntiles; ++j) {
-            const int s = j % TC_STAGES;
-            mbar_wait(bar_p, (uint32_t)j & 1u);
-            tc_fence_after();
-            if (lane == 0) {
+            if (ntiles > 1) issue_qk(1);
+            for (int j = 0; j < ntiles; ++j) {
+                const int s = j % TC_STAGES, b = j & 1;
+                mbar_wait(bar_p + 8 * b, (uint32_t)(j >> 1) & 1u);
+                tc_fence_after();
                 const uint64_t descV = umma_desc_sw64(sKV + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+                const uint32_t pa = tmem + (uint32_t)(b * TC_BN);
 #pragma unroll
                 for (int kk = 0; kk < TC_BN / 16; ++kk)  // 16 keys per step: 8 TMEM columns of P, 1 KB of V
-                    umma_ts(tmem + TC_COL_O, tmem + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
+                    umma_ts(tmem + TC_COL_O, pa + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
                 tc_commit(bar_kv_empty + 8 * s);
+                tc_commit(bar_pv);
+                if (j + 2 < ntiles) issue_qk(j + 2);
             }
-            __syncwarp();
-            if (j + 1 < ntiles) {
-                const int s1 = (j + 1) % TC_STAGES;
-                mbar_wait(bar_kv_full + 8 * s1, (uint32_t)((j + 1) / TC_STAGES) & 1u);
-                tc_fence_after();
-                if (lane == 0) {
-                    issue_qk(s1);
-                    tc_commit(bar_s);
-                }
-            } else if (lane == 0) {
-                tc_commit(bar_o);
-            }
-            __syncwarp();
+            tc_commit(bar_o);
         }
     } else {
         // ================= softmax warps: thread = query row = TMEM lane =================
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
-        float m_ref = -INFINITY, l = 0.f;
-        uint32_t sv[4][32];
+        float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f;
         for (int j = 0; j < ntiles; ++j) {
-            mbar_wait(bar_s, (uint32_t)j & 1u);
+            const int b = j & 1;
+            const uint32_t scol = trow + (uint32_t)(b * TC_BN);
+            mbar_wait(bar_s + 8 * b, (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
-#pragma unroll
-            for (int c = 0; c < 4; ++c) tmem_ld32(trow + c * 32, sv[c]);
+            uint32_t sv[2][32];
+            tmem_ld32(scol, sv[0]);
+            tmem_ld32(scol + 32, sv[1]);
             tmem_wait_ld();
             const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
             if (nvalid < TC_BN) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
+                for (int c = 0; c < 2; ++c)
 #pragma unroll
                     for (int i = 0; i < 32; ++i)
                         if (c * 32 + i >= nvalid) sv[c][i] = 0xff800000u;  // -inf
             }
-            float mx = -INFINITY;
+            float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(sv[c][i]));
-            const float mt = mx * sc;
+            for (int i = 0; i < 32; ++i) {
+                mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
+                mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+            }
+            const float mt = fmaxf(mx0, mx1) * sc;
             if (j == 0) {
                 m_ref = mt;
             } else {
@@ -263,7 +268,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 if (__any_sync(0xffffffffu, need)) {
                     const float corr = need ? fast_exp2(m_ref - mt) : 1.0f;
                     if (need) m_ref = mt;
-                    l *= corr;
+                    l0 *= corr;
+                    l1 *= corr;
+                    mbar_wait(bar_pv, (uint32_t)(j - 1) & 1u);  // O += P_{j-1} V_{j-1} must have landed
+                    tc_fence_after();
                     uint32_t ov[32];
                     tmem_ld32(trow + TC_COL_O, ov);
                     tmem_wait_ld();
@@ -272,22 +280,20 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     tmem_st32(trow + TC_COL_O, ov);
                 }
             }
+            uint32_t pk[32];
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
-                uint32_t pk[32];
-#pragma unroll
-                for (int i = 0; i < 32; ++i) {
-                    const int cc = 2 * c + (i >> 4), ii = (2 * i) & 31;
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii]), sc, -m_ref));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii + 1]), sc, -m_ref));
-                    l += p0 + p1;
-                    pk[i] = pack_bf16x2(p0, p1);
-                }
-                tmem_st32(trow + c * 32, pk);
+            for (int i = 0; i < 32; ++i) {
+                const int cc = i >> 4, ii = (2 * i) & 31;
+                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii]), sc, -m_ref));
+                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii + 1]), sc, -m_ref));
+                l0 += p0;
+                l1 += p1;
+                pk[i] = pack_bf16x2(p0, p1);
             }
+            tmem_st32(scol, pk);
             tmem_wait_st();
             tc_fence_before();
-            mbar_arrive(bar_p);
+            mbar_arrive(bar_p + 8 * b);
         }
         // ---- epilogue: O / l -> bf16 -> global ----
         mbar_wait(bar_o, 0);
@@ -297,7 +303,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         tmem_wait_ld();
         const int64_t r = m0 + warp * 32 + lane;
         if (r < p.R) {
-            const float inv = 1.0f / l;
+            const float inv = 1.0f / (l0 + l1);
             uint4* dst = reinterpret_cast<uint4*>(p.O + r * p.o_row + (int64_t)t * p.o_tok + h * kDh);
 #pragma unroll
             for (int q = 0; q < 4; ++q) {

@@ -209,8 +209,14 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
         g.Cb = c->qkv; g.ldcb = 3 * kE;
         if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
         {
-            const unsigned blocks = (unsigned)std::min<int64_t>(R, 148 * 16);
-            feature_attn_kernel<<<blocks, FA_WARPS * 32, fa_smem, st>>>(c->qkv, R, T, c->ob);
+            TimeScope ts(c, st, KC_OTHER, 4.0 * (double)R * T * T * kE);
+            if (T <= 16) {
+                feature_attn_mma_kernel<<<(unsigned)ceil_div(R * kHeads, FAM_WARPS), FAM_WARPS * 32, 0, st>>>(c->qkv, R, T,
+                                                                                                           c->ob);
+            } else {
+                const unsigned blocks = (unsigned)std::min<int64_t>(R, 148 * 16);
+                feature_attn_kernel<<<blocks, FA_WARPS * 32, fa_smem, st>>>(c->qkv, R, T, c->ob);
+            }
             PFN_LAUNCH_OK(c);
         }
         g.A = c->ob; g.W = wb + o.feat_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;

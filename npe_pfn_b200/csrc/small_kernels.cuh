@@ -220,6 +220,90 @@ __global__ void __launch_bounds__(FA_WARPS * 32) feature_attn_kernel(const bf16*
     }
 }
 
+// Tensor-core version for T <= 16 (F <= 30 features): one warp per (row, head), the whole T x T attention is
+// one 16 x 16 tile: S = Q K^T is 2 n-tiles x 2 k-steps of m16n8k16, O = P V is 4 n-tiles x 1 k-step.  Fragments
+// are loaded straight from global memory (the row's q/k/v are 64-byte runs), softmax on the accumulator quads.
+constexpr int FAM_WARPS = 8;
+__global__ void __launch_bounds__(FAM_WARPS * 32) feature_attn_mma_kernel(const bf16* __restrict__ qkv, int64_t R, int T,
+                                                                          bf16* __restrict__ out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int64_t w = (int64_t)blockIdx.x * FAM_WARPS + warp;
+    if (w >= R * kHeads) return;
+    const int64_t r = w / kHeads;
+    const int h = (int)(w % kHeads);
+    const bf16* base = qkv + r * T * 3 * kE + h * kDh;
+    const int64_t ts = 3 * kE;  // token stride
+    const int q0 = min(g, T - 1), q1 = min(g + 8, T - 1);
+    auto ld32 = [](const bf16* ptr) { return *reinterpret_cast<const uint32_t*>(ptr); };
+    // S = Q K^T
+    float s[2][4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < 2; ++kk) {
+        uint32_t a[4];
+        a[0] = ld32(base + q0 * ts + 16 * kk + 2 * tq);
+        a[1] = ld32(base + q1 * ts + 16 * kk + 2 * tq);
+        a[2] = ld32(base + q0 * ts + 16 * kk + 8 + 2 * tq);
+        a[3] = ld32(base + q1 * ts + 16 * kk + 8 + 2 * tq);
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const int key = min(8 * n + g, T - 1);
+            const uint32_t b0 = ld32(base + key * ts + kE + 16 * kk + 2 * tq);
+            const uint32_t b1 = ld32(base + key * ts + kE + 16 * kk + 8 + 2 * tq);
+            mma_bf16_16816(s[n], a, b0, b1);
+        }
+    }
+    const float sc = 0.17677669529663687f * 1.4426950408889634f;
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        const int key = 8 * n + 2 * tq;
+        if (key >= T) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+        if (key + 1 >= T) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+        mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+        mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+    }
+    float l[2] = {0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+        mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+        mx[i] *= sc;
+    }
+    uint32_t pa[4];
+#pragma unroll
+    for (int n = 0; n < 2; ++n) {
+        const float p0 = exp2f(fmaf(s[n][0], sc, -mx[0])), p1 = exp2f(fmaf(s[n][1], sc, -mx[0]));
+        const float p2 = exp2f(fmaf(s[n][2], sc, -mx[1])), p3 = exp2f(fmaf(s[n][3], sc, -mx[1]));
+        l[0] += p0 + p1;
+        l[1] += p2 + p3;
+        pa[2 * n + 0] = pack_bf16x2(p0, p1);
+        pa[2 * n + 1] = pack_bf16x2(p2, p3);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        l[i] += __shfl_xor_sync(0xffffffffu, l[i], 1);
+        l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
+    }
+    // O = P V : B fragment (k = key, n = dh) gathered as two 16-bit loads per register
+    const unsigned short* vb = reinterpret_cast<const unsigned short*>(base + 2 * kE);
+    const int k0 = min(2 * tq, T - 1), k1 = min(2 * tq + 1, T - 1), k2 = min(2 * tq + 8, T - 1), k3 = min(2 * tq + 9, T - 1);
+    const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int dh = 8 * j + g;
+        const uint32_t b0 = (uint32_t)vb[k0 * ts + dh] | ((uint32_t)vb[k1 * ts + dh] << 16);
+        const uint32_t b1 = (uint32_t)vb[k2 * ts + dh] | ((uint32_t)vb[k3 * ts + dh] << 16);
+        float o[4] = {0.f, 0.f, 0.f, 0.f};
+        mma_bf16_16816(o, pa, b0, b1);
+        const int col = h * kDh + 8 * j + 2 * tq;
+        if (g < T) *reinterpret_cast<uint32_t*>(out + (r * T + g) * kE + col) = pack_bf16x2(o[0] * inv0, o[1] * inv0);
+        if (g + 8 < T) *reinterpret_cast<uint32_t*>(out + (r * T + g + 8) * kE + col) = pack_bf16x2(o[2] * inv1, o[3] * inv1);
+    }
+}
+
 // head-0 K/V of the context rows -> cache [T][N][64] (K 0..31 | V 32..63) for one layer
 __global__ void kv_cache_kernel(const bf16* __restrict__ qkv, int64_t N, int T, bf16* __restrict__ cache) {
     // one thread per 16 bytes: (n, t, part in 0..7): parts 0-3 = K, 4-7 = V
