@@ -63,8 +63,8 @@ const char* pfn_last_error(void);
 int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_floats, int device,
                    void* stream, pfn_ctx** out);
 int pfn_ctx_destroy(pfn_ctx* ctx);
-/* runtime switches (no reference counterpart): "attn_impl" 0 = warp-level mma.sync item attention,
- * 1 = tcgen05/TMEM item attention (default); "chunk_rows" = test rows per pass; "time_kernels" 1 = record a
+/* runtime switches (no reference counterpart): "attn_impl" / "gemm_impl" 0 = warp-level mma.sync kernels,
+ * 1 = tcgen05/TMEM/TMA kernels (default); "chunk_rows" = test rows per pass; "time_kernels" 1 = record a
  * CUDA event pair around every attention / GEMM launch on its stream (read back with pfn_kernel_times). */
 int pfn_set_option(pfn_ctx* ctx, const char* key, int64_t value);
 

@@ -20,6 +20,9 @@
 #endif
 #include "common.cuh"
 #include "gemm_mma.cuh"
+#ifdef PFN_WITH_ATTN_TC
+#include "gemm_tc.cuh"
+#endif
 #include "small_kernels.cuh"
 
 namespace pfn {
@@ -74,6 +77,8 @@ struct pfn_ctx {
     int64_t last_rows = 0;
     int last_T = 0;
     int attn_impl = 1;  // 0 = mma.sync, 1 = tcgen05
+    int gemm_impl = 1;  // 0 = mma.sync, 1 = tcgen05
+    int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
     int time_kernels = 0;
     struct Timed { cudaEvent_t a, b; int cls; double flops; };
@@ -158,6 +163,11 @@ struct TimeScope {  // records an event pair around the launches issued inside i
 template <int EPI>
 int gemm(pfn_ctx* c, const GemmArgs& a, cudaStream_t st) {
     TimeScope ts(c, st, KC_GEMM, 2.0 * (double)a.M * a.N * a.K);
+#ifdef PFN_WITH_ATTN_TC
+    if (c->gemm_impl == 1) {
+        PFN_CUDA_OK(launch_gemm_tc<EPI>(a, c->num_sms, st));
+    } else
+#endif
     PFN_CUDA_OK(launch_gemm_mma<EPI>(a, st));
     c->launches++;
     return 0;
@@ -326,6 +336,7 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
     PFN_CUDA_OK(cudaGetDeviceProperties(&prop, device));
     PFN_REQUIRE(prop.major == 10, "npe_pfn_b200 kernels are built for sm_100a (Blackwell B200) only");
     pfn_ctx* c = new pfn_ctx();
+    c->num_sms = prop.multiProcessorCount;
     c->cfg = *cfg;
     c->device = device;
     c->off = make_offsets(*cfg);
@@ -335,6 +346,7 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
         return 2;
     }
     if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
+    if (const char* e = getenv("NPE_PFN_B200_GEMM")) c->gemm_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
     PFN_CUDA_OK(cudaMalloc(&c->wf, n_floats * 4));
     PFN_CUDA_OK(cudaMalloc(&c->wb, n_floats * 2));
     PFN_CUDA_OK(cudaMemcpyAsync(c->wf, weights, n_floats * 4, cudaMemcpyDeviceToDevice, st));
@@ -373,6 +385,7 @@ int pfn_ctx_destroy(pfn_ctx* c) {
 int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     PFN_REQUIRE(c && key, "null argument");
     if (!strcmp(key, "attn_impl")) { c->attn_impl = (int)value; return 0; }
+    if (!strcmp(key, "gemm_impl")) { c->gemm_impl = (int)value; return 0; }
     if (!strcmp(key, "chunk_rows")) { c->cfg.chunk_rows = (int)value; return 0; }
     if (!strcmp(key, "time_kernels")) { c->time_kernels = (int)value; return 0; }
     last_error() = std::string("unknown option ") + key;
@@ -417,7 +430,8 @@ int pfn_forward_logits(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_
     PFN_REQUIRE(X && out, "null data pointer");
     Slot& s = c->slots[slot];
     PFN_REQUIRE(ldx >= s.F, "row stride smaller than the slot's feature count");
-    PFN_REQUIRE(ld_out >= c->cfg.num_buckets && ld_out % 2 == 0, "logits row stride must be even and >= num_buckets");
+    PFN_REQUIRE(ld_out >= c->cfg.num_buckets && ld_out % 4 == 0, "logits row stride must be a multiple of 4 and >= num_buckets");
+    PFN_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "logits buffer must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     PFN_CUDA_OK(cudaSetDevice(c->device));
     if (int rc = ensure_decoder_ws(c)) return rc;

@@ -1,0 +1,321 @@
+// Dense projections of the per-feature transformer on the 5th-generation tensor cores (tcgen05 + TMEM + TMA):
+//   C[M, N] = A[M, K] (bf16, row stride lda) x W[N, K]^T (bf16), fp32 accumulation in TMEM,
+// with the layer's element-wise work fused into the epilogue (same four variants as gemm_mma.cuh):
+//   EPI_BF16            -> bf16                              (QKV / Q projections)
+//   EPI_BIAS_GELU_BF16  -> gelu(acc + bias) as bf16          (MLP up-projection, decoder hidden)
+//   EPI_RESID_LN        -> LayerNorm(acc + residual), fp32 residual stream in/out + bf16 copy (N == 192)
+//   EPI_BIAS_SCALE_F32  -> (acc + bias) * scale as fp32      (decoder logits / temperature)
+//
+// Persistent, warp-specialised, one CTA per SM (320 threads):
+//   warps 0-3 / 4-7  two epilogue warpgroups, alternating over the CTA's tiles (thread = output row = TMEM lane):
+//                    tcgen05.ld the 128 x 192 fp32 accumulator, apply the epilogue, store straight to global;
+//   warp 8           TMA producer: A (128 x 64) and W (192 x 64) k-blocks, 128-byte swizzle, 4-stage mbarrier ring;
+//   warp 9           TMEM allocation (2 x 256 columns = two accumulators) + single-thread tcgen05.mma issue
+//                    (M128 N192 K16, four per k-block), tcgen05.commit frees the stage / publishes the accumulator.
+// While one warpgroup drains accumulator b, the tensor pipe already fills accumulator b^1.
+#pragma once
+#include <cuda.h>
+
+#include "attn_tc.cuh"
+#include "common.cuh"
+#include "gemm_mma.cuh"
+
+namespace pfn {
+
+constexpr int GT_BM = 128, GT_BN = 192, GT_BK = 64, GT_STAGES = 4, GT_THREADS = 320;
+constexpr int GT_A_BYTES = GT_BM * GT_BK * 2;   // 16 KB
+constexpr int GT_B_BYTES = GT_BN * GT_BK * 2;   // 24 KB
+constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
+constexpr int GT_SMEM_BYTES = 1024 + GT_STAGES * GT_STAGE_BYTES + 256;
+constexpr int GT_TMEM_COLS = 512, GT_ACC_STRIDE = 256;
+
+struct GemmTcArgs {
+    int64_t M;
+    int N, K;
+    bf16* Cb;
+    int64_t ldcb;
+    float* Cf;
+    int64_t ldcf;
+    const float* bias;
+    float scale, ln_eps;
+    int n_chunks;
+    int64_t tiles;
+};
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1) : "memory");
+}
+// K-major tile with 128-byte rows, 128-byte swizzle: 8-row groups are 1024 B apart
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;  // SWIZZLE_128B
+    return d;
+}
+
+// erf by Abramowitz & Stegun 7.1.26 (|error| < 7e-7 in fp32): one rcp + one ex2 + 8 FMA-pipe operations
+__device__ __forceinline__ float gelu_fast(float x) {
+    const float z = x * 0.70710678118654752440f;
+    const float a = fabsf(z);
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
+    float pl = fmaf(1.061405429f, t, -1.453152027f);
+    pl = fmaf(pl, t, 1.421413741f);
+    pl = fmaf(pl, t, -0.284496736f);
+    pl = fmaf(pl, t, 0.254829592f);
+    pl *= t;
+    const float e = fast_exp2(-a * a * 1.4426950408889634f);
+    const float erf_abs = fmaf(-pl, e, 1.0f);
+    const float erf = copysignf(erf_abs, z);
+    return 0.5f * x * (1.0f + erf);
+}
+
+template <int EPI>
+__device__ __forceinline__ void gemm_tc_epilogue(const GemmTcArgs& p, uint32_t tacc, int64_t row, int n0) {
+    const bool row_ok = row < p.M;
+    if (EPI == EPI_RESID_LN) {
+        // N == 192: the thread owns a complete row.  Pass 1: x = acc + residual, sums, x parked back in TMEM.
+        float* xr = p.Cf + row * p.ldcf;
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < GT_BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(tacc + c * 32, v);
+            tmem_wait_ld();
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                float4 r4 = row_ok ? *reinterpret_cast<const float4*>(xr + c * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float x0 = __uint_as_float(v[4 * q + 0]) + r4.x, x1 = __uint_as_float(v[4 * q + 1]) + r4.y;
+                const float x2 = __uint_as_float(v[4 * q + 2]) + r4.z, x3 = __uint_as_float(v[4 * q + 3]) + r4.w;
+                s1 += (x0 + x1) + (x2 + x3);
+                s2 = fmaf(x0, x0, s2); s2 = fmaf(x1, x1, s2); s2 = fmaf(x2, x2, s2); s2 = fmaf(x3, x3, s2);
+                v[4 * q + 0] = __float_as_uint(x0); v[4 * q + 1] = __float_as_uint(x1);
+                v[4 * q + 2] = __float_as_uint(x2); v[4 * q + 3] = __float_as_uint(x3);
+            }
+            tmem_st32(tacc + c * 32, v);
+        }
+        tmem_wait_st();
+        const float mu = s1 * (1.0f / kE);
+        const float var = fmaxf(s2 * (1.0f / kE) - mu * mu, 0.f);
+        const float rs = rsqrtf(var + p.ln_eps);
+        bf16* br = p.Cb + row * p.ldcb;
+#pragma unroll 1
+        for (int c = 0; c < GT_BN / 32; ++c) {
+            uint32_t v[32];
+            __syncwarp();
+            tmem_ld32(tacc + c * 32, v);
+            tmem_wait_ld();
+            if (row_ok) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float y[8];
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = (__uint_as_float(v[8 * q + i]) - mu) * rs;
+                    *reinterpret_cast<float4*>(xr + c * 32 + 8 * q) = make_float4(y[0], y[1], y[2], y[3]);
+                    *reinterpret_cast<float4*>(xr + c * 32 + 8 * q + 4) = make_float4(y[4], y[5], y[6], y[7]);
+                    uint4 o;
+                    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+                    o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+                    *reinterpret_cast<uint4*>(br + c * 32 + 8 * q) = o;
+                }
+            }
+        }
+        return;
+    }
+#pragma unroll 1
+    for (int c = 0; c < GT_BN / 32; ++c) {
+        uint32_t v[32];
+        __syncwarp();
+        tmem_ld32(tacc + c * 32, v);
+        tmem_wait_ld();
+        const int col0 = n0 + c * 32;
+        const bool live = row_ok && col0 < p.N;  // the TMEM load above stays warp-uniform; only stores are guarded
+        if (live && EPI == EPI_BIAS_SCALE_F32) {
+            float* dst = p.Cf + row * p.ldcf + col0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int col = col0 + 4 * q;
+                if (col + 3 < p.N) {
+                    const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
+                    float4 o;
+                    o.x = (__uint_as_float(v[4 * q + 0]) + b4.x) * p.scale;
+                    o.y = (__uint_as_float(v[4 * q + 1]) + b4.y) * p.scale;
+                    o.z = (__uint_as_float(v[4 * q + 2]) + b4.z) * p.scale;
+                    o.w = (__uint_as_float(v[4 * q + 3]) + b4.w) * p.scale;
+                    *reinterpret_cast<float4*>(dst + 4 * q) = o;
+                } else {
+                    for (int i = 0; i < 4; ++i)
+                        if (col + i < p.N) dst[4 * q + i] = (__uint_as_float(v[4 * q + i]) + p.bias[col + i]) * p.scale;
+                }
+            }
+        } else if (live) {
+            bf16* dst = p.Cb + row * p.ldcb + col0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                float y[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) y[i] = __uint_as_float(v[8 * q + i]);
+                if (EPI == EPI_BIAS_GELU_BF16) {
+                    if (p.bias) {
+                        const float4 b0 = *reinterpret_cast<const float4*>(p.bias + col0 + 8 * q);
+                        const float4 b1 = *reinterpret_cast<const float4*>(p.bias + col0 + 8 * q + 4);
+                        y[0] += b0.x; y[1] += b0.y; y[2] += b0.z; y[3] += b0.w;
+                        y[4] += b1.x; y[5] += b1.y; y[6] += b1.z; y[7] += b1.w;
+                    }
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) y[i] = gelu_fast(y[i]);
+                }
+                uint4 o;
+                o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
+                o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
+                *reinterpret_cast<uint4*>(dst + 8 * q) = o;
+            }
+        }
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(GT_THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcArgs p) {
+    extern __shared__ uint8_t gt_smem_raw[];
+    const uint32_t raw = smem_u32(gt_smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bars = base + GT_STAGES * GT_STAGE_BYTES;
+    const uint32_t bar_full = bars;                      // [GT_STAGES]
+    const uint32_t bar_empty = bars + 8 * GT_STAGES;     // [GT_STAGES]
+    const uint32_t bar_acc_full = bars + 16 * GT_STAGES;   // [2]
+    const uint32_t bar_acc_empty = bar_acc_full + 16;      // [2]
+    const uint32_t tmem_slot = bar_acc_full + 32;
+    uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gt_smem_raw + (tmem_slot - raw));
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kblocks = p.K / GT_BK;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < GT_STAGES; ++s) {
+            mbar_init(bar_full + 8 * s, 1);
+            mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(bar_acc_full + 8 * b, 1);
+            mbar_init(bar_acc_empty + 8 * b, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 9) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
+                     "r"((uint32_t)GT_TMEM_COLS) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot_ptr;
+
+    if (warp == 8) {
+        // ================= TMA producer =================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmA)) : "memory");
+            asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmW)) : "memory");
+            uint32_t it = 0;
+            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
+                const int m_blk = (int)(tile / p.n_chunks), n_blk = (int)(tile % p.n_chunks);
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % GT_STAGES, ph = (it / GT_STAGES) & 1u;
+                    mbar_wait(bar_empty + 8 * s, ph ^ 1u);
+                    mbar_expect_tx(bar_full + 8 * s, GT_STAGE_BYTES);
+                    const uint32_t dA = base + s * GT_STAGE_BYTES, dB = dA + GT_A_BYTES;
+                    tma_load_2d(dA, &tmA, bar_full + 8 * s, kb * GT_BK, m_blk * GT_BM);
+                    tma_load_2d(dB, &tmW, bar_full + 8 * s, kb * GT_BK, n_blk * GT_BN);
+                }
+            }
+        }
+    } else if (warp == 9) {
+        // ================= MMA issuer (one thread) =================
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_bf16(GT_BM, GT_BN, 0, 0);
+            uint32_t it = 0, lt = 0;
+            for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+                const uint32_t b = lt & 1u;
+                mbar_wait(bar_acc_empty + 8 * b, ((lt >> 1) & 1u) ^ 1u);  // epilogue has drained accumulator b
+                tc_fence_after();
+                const uint32_t d = tmem + b * GT_ACC_STRIDE;
+                for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                    const uint32_t s = it % GT_STAGES, ph = (it / GT_STAGES) & 1u;
+                    mbar_wait(bar_full + 8 * s, ph);
+                    tc_fence_after();
+                    const uint64_t dA = umma_desc_sw128(base + s * GT_STAGE_BYTES);
+                    const uint64_t dB = umma_desc_sw128(base + s * GT_STAGE_BYTES + GT_A_BYTES);
+#pragma unroll
+                    for (int kk = 0; kk < GT_BK / 16; ++kk)  // 32 bytes per K16 step inside the 128-byte swizzle atom
+                        umma_ss(d, dA + (uint64_t)(2 * kk), dB + (uint64_t)(2 * kk), idesc, (kb > 0) || (kk > 0));
+                    tc_commit(bar_empty + 8 * s);
+                }
+                tc_commit(bar_acc_full + 8 * b);
+            }
+        }
+    } else {
+        // ================= epilogue warpgroups =================
+        const uint32_t e = (uint32_t)warp >> 2;  // warpgroup 0 / 1 <-> accumulator 0 / 1
+        const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+        uint32_t lt = 0;
+        for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
+            if ((lt & 1u) != e) continue;
+            const int m_blk = (int)(tile / p.n_chunks), n_blk = (int)(tile % p.n_chunks);
+            mbar_wait(bar_acc_full + 8 * e, (lt >> 1) & 1u);
+            tc_fence_after();
+            const uint32_t tacc = tmem + (lane_base << 16) + e * GT_ACC_STRIDE;
+            gemm_tc_epilogue<EPI>(p, tacc, (int64_t)m_blk * GT_BM + lane_base + lane, n_blk * GT_BN);
+            tc_fence_before();
+            mbar_arrive(bar_acc_empty + 8 * e);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) {
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)GT_TMEM_COLS)
+                     : "memory");
+    }
+}
+
+// 2-D bf16 map (inner = K elements), 128-byte swizzle, box = 64 x rows
+static inline bool make_map2_sw128(CUtensorMap* m, const void* base, uint64_t inner, uint64_t rows, uint64_t row_bytes,
+                                   uint32_t box_rows) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {inner, rows};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {(cuuint32_t)GT_BK, box_rows};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+template <int EPI>
+static inline cudaError_t launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st) {
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    if (a.K % GT_BK != 0 || (EPI == EPI_RESID_LN && a.N != GT_BN)) return cudaErrorInvalidValue;
+    CUtensorMap mA, mW;
+    if (!make_map2_sw128(&mA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, GT_BM)) return cudaErrorInvalidValue;
+    if (!make_map2_sw128(&mW, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, GT_BN)) return cudaErrorInvalidValue;
+    GemmTcArgs p{};
+    p.M = a.M; p.N = a.N; p.K = a.K; p.Cb = a.Cb; p.ldcb = a.ldcb; p.Cf = a.Cf; p.ldcf = a.ldcf; p.bias = a.bias;
+    p.scale = a.scale; p.ln_eps = a.ln_eps;
+    p.n_chunks = (a.N + GT_BN - 1) / GT_BN;
+    p.tiles = ceil_div(a.M, GT_BM) * p.n_chunks;
+    const unsigned grid = (unsigned)std::min<int64_t>(p.tiles, num_sms);
+    gemm_tc_kernel<EPI><<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(mA, mW, p);
+    return cudaGetLastError();
+}
+
+}  // namespace pfn

@@ -257,6 +257,25 @@ def test_item_attention_impls_agree(engine):
     assert d.max() <= LOGIT_ATOL
 
 
+def test_gemm_impls_agree(engine):
+    """tcgen05 projections (fused LayerNorm / GELU / bias epilogues) against the warp-level mma.sync GEMMs."""
+    g = torch.Generator().manual_seed(44)
+    N, F, M = 700, 6, 900
+    Xc = torch.randn(N, F, generator=g)
+    yc = Xc[:, 2] - Xc[:, 0] + 0.1 * torch.randn(N, generator=g)
+    Xt = torch.randn(M, F, generator=g)
+    outs = []
+    for impl in (0, 1):
+        engine.set_option("gemm_impl", impl)
+        engine.prefill(5, Xc, yc)
+        outs.append(engine.forward_logits(5, Xt))
+    engine.set_option("gemm_impl", 1)
+    d = (outs[0] - outs[1]).abs()
+    print(f"mma vs tcgen05 GEMMs: max|dlogit|={d.max():.4f} mean={d.mean():.5f}")
+    assert torch.isfinite(outs[1]).all()
+    assert d.max() <= LOGIT_ATOL and d.mean() <= LOGIT_MEAN_ATOL
+
+
 # ---- reference-facing API (shapes / errors as in /root/reference/tests/test_npe_pfn.py) -------------------
 def test_api_sample_logprob_shapes_and_errors(engine):
     from npe_pfn_b200 import BoxUniform, TabPFN_Based_NPE_PFN
