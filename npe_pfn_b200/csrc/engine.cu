@@ -64,7 +64,11 @@ struct pfn_ctx {
     int64_t cap_tok = 0;
     uint8_t* ws = nullptr;
     float* xf = nullptr;
-    bf16 *xb = nullptr, *qkv = nullptr, *ob = nullptr, *hb = nullptr;
+    bf16 *xb = nullptr, *qkv = nullptr, *ob = nullptr;
+    // sub-chunk scratch (reused so that it stays L2 resident): feature-attention qkv and MLP hidden
+    bf16 *qkv_s = nullptr, *hb_s = nullptr;
+    int64_t sub_tok = 0;      // scratch capacity in tokens
+    int64_t sub_tok_opt = 0;  // option "sub_tokens": 0 = the whole chunk in one go
     // decoder / head workspace
     int dec_rows = 4096;
     bf16* dech = nullptr;
@@ -127,14 +131,18 @@ int ensure_workspace(pfn_ctx* c, int64_t tokens, cudaStream_t st) {
     c->ws = nullptr;
     c->cap_tok = 0;
     const int64_t cap = tokens + 1024;
-    const size_t per_tok = (size_t)kE * 4 + kE * 2 + 3 * kE * 2 + kE * 2 + kHid * 2;
-    PFN_CUDA_OK(cudaMalloc(&c->ws, per_tok * (size_t)cap + 1024));
+    c->sub_tok = cap;
+    const size_t per_tok = (size_t)kE * 4 + kE * 2 + 3 * kE * 2 + kE * 2;
+    const size_t scratch = (size_t)(c->sub_tok + 128) * (3 * kE + kHid) * 2;
+    PFN_CUDA_OK(cudaMalloc(&c->ws, per_tok * (size_t)cap + scratch + 4096));
     uint8_t* p = c->ws;
     c->xf = reinterpret_cast<float*>(p); p += (size_t)cap * kE * 4;
     c->xb = reinterpret_cast<bf16*>(p);  p += (size_t)cap * kE * 2;
     c->qkv = reinterpret_cast<bf16*>(p); p += (size_t)cap * 3 * kE * 2;
     c->ob = reinterpret_cast<bf16*>(p);  p += (size_t)cap * kE * 2;
-    c->hb = reinterpret_cast<bf16*>(p);
+    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 1023) & ~(uintptr_t)1023);
+    c->qkv_s = reinterpret_cast<bf16*>(p); p += (size_t)(c->sub_tok + 128) * 3 * kE * 2;
+    c->hb_s = reinterpret_cast<bf16*>(p);
     c->cap_tok = cap;
     return 0;
 }
@@ -211,61 +219,79 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
         fa_smem_set = fa_smem;
     }
 
-    for (int l = 0; l < L; ++l) {
+    // The chain between two item-attention kernels runs sub-chunk by sub-chunk (one wave of 128-token tiles), so
+    // its intermediates (feature-attention qkv, MLP hidden) live in small reused scratch buffers that stay in L2;
+    // only the residual stream, the item queries and the attention output cross HBM once per layer.
+    const int64_t sub_rows = c->sub_tok_opt > 0 ? std::max<int64_t>(1, std::min(c->sub_tok_opt, c->sub_tok) / T) : R;
+    auto first_half = [&](int l, int64_t r0, int64_t nr) -> int {  // feature attention + item-attention projections
+        const int64_t t0 = r0 * T, ntok = nr * T;
         GemmArgs g{};
         g.ln_eps = c->cfg.ln_eps;
-        // ---- attention between features -------------------------------------------------------------
-        g.A = c->xb; g.lda = kE; g.W = wb + o.feat_wqkv + (size_t)l * 3 * kE * kE; g.M = tok; g.N = 3 * kE; g.K = kE;
-        g.Cb = c->qkv; g.ldcb = 3 * kE;
+        g.A = c->xb + t0 * kE; g.lda = kE; g.W = wb + o.feat_wqkv + (size_t)l * 3 * kE * kE; g.M = ntok; g.N = 3 * kE; g.K = kE;
+        g.Cb = c->qkv_s; g.ldcb = 3 * kE;
         if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
         {
-            TimeScope ts(c, st, KC_OTHER, 4.0 * (double)R * T * T * kE);
+            TimeScope ts(c, st, KC_OTHER, 4.0 * (double)nr * T * T * kE);
             if (T <= 16) {
-                feature_attn_mma_kernel<<<(unsigned)ceil_div(R * kHeads, FAM_WARPS), FAM_WARPS * 32, 0, st>>>(c->qkv, R, T,
-                                                                                                           c->ob);
+                feature_attn_mma_kernel<<<(unsigned)ceil_div(nr * kHeads, FAM_WARPS), FAM_WARPS * 32, 0, st>>>(
+                    c->qkv_s, nr, T, c->ob + t0 * kE);
             } else {
-                const unsigned blocks = (unsigned)std::min<int64_t>(R, 148 * 16);
-                feature_attn_kernel<<<blocks, FA_WARPS * 32, fa_smem, st>>>(c->qkv, R, T, c->ob);
+                const unsigned blocks = (unsigned)std::min<int64_t>(nr, 148 * 16);
+                feature_attn_kernel<<<blocks, FA_WARPS * 32, fa_smem, st>>>(c->qkv_s, nr, T, c->ob + t0 * kE);
             }
             PFN_LAUNCH_OK(c);
         }
-        g.A = c->ob; g.W = wb + o.feat_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;
-        g.Cb = c->xb; g.ldcb = kE; g.Cf = c->xf; g.ldcf = kE;
+        g.A = c->ob + t0 * kE; g.W = wb + o.feat_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;
+        g.Cb = c->xb + t0 * kE; g.ldcb = kE; g.Cf = c->xf + t0 * kE; g.ldcf = kE;
         if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+        g.A = c->xb + t0 * kE; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.K = kE; g.Cf = nullptr;
+        if (ctx_rows) {
+            g.N = 3 * kE; g.Cb = c->qkv + t0 * 3 * kE; g.ldcb = 3 * kE;
+            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
+            bf16* cache_l = s.kv + (size_t)l * T * s.N * kKvRow;
+            kv_cache_kernel<<<(unsigned)ceil_div(ntok * 8, 256), 256, 0, st>>>(c->qkv + t0 * 3 * kE, nr, T, r0, s.N, cache_l);
+            PFN_LAUNCH_OK(c);
+        } else {
+            g.N = kE; g.Cb = c->qkv + t0 * kE; g.ldcb = kE;  // Q rows of the projection only
+            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
+        }
+        return 0;
+    };
+    auto second_half = [&](int l, int64_t r0, int64_t nr) -> int {  // item out-projection + MLP
+        const int64_t t0 = r0 * T, ntok = nr * T;
+        GemmArgs g{};
+        g.ln_eps = c->cfg.ln_eps;
+        g.A = c->ob + t0 * kE; g.lda = kE; g.W = wb + o.item_wo + (size_t)l * kE * kE; g.M = ntok; g.N = kE; g.K = kE;
+        g.Cb = c->xb + t0 * kE; g.ldcb = kE; g.Cf = c->xf + t0 * kE; g.ldcf = kE;
+        if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+        g.A = c->xb + t0 * kE; g.W = wb + o.mlp_w1 + (size_t)l * kHid * kE; g.N = kHid; g.K = kE;
+        g.Cb = c->hb_s; g.ldcb = kHid; g.Cf = nullptr; g.bias = nullptr;
+        if (int rc = gemm<EPI_BIAS_GELU_BF16>(c, g, st)) return rc;
+        g.A = c->hb_s; g.lda = kHid; g.W = wb + o.mlp_w2 + (size_t)l * kE * kHid; g.N = kE; g.K = kHid;
+        g.Cb = c->xb + t0 * kE; g.ldcb = kE; g.Cf = c->xf + t0 * kE; g.ldcf = kE;
+        return gemm<EPI_RESID_LN>(c, g, st);
+    };
 
-        // ---- attention between items ------------------------------------------------------------------
+    for (int64_t r0 = 0; r0 < R; r0 += sub_rows)
+        if (int rc = first_half(0, r0, std::min(sub_rows, R - r0))) return rc;
+    for (int l = 0; l < L; ++l) {
         AttnArgs a{};
         a.R = R; a.N = s.N;
         a.O = c->ob; a.o_row = (int64_t)T * kE; a.o_tok = kE;
-        bf16* cache_l = s.kv + (size_t)l * T * s.N * kKvRow;
         if (ctx_rows) {
-            g.A = c->xb; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.N = 3 * kE; g.K = kE;
-            g.Cb = c->qkv; g.ldcb = 3 * kE; g.Cf = nullptr;
-            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
-            const int64_t total = R * T * 8;
-            kv_cache_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(c->qkv, R, T, cache_l);
-            PFN_LAUNCH_OK(c);
             a.Q = c->qkv; a.q_row = (int64_t)T * 3 * kE; a.q_tok = 3 * kE;
             a.K = c->qkv + kE; a.k_tok = 3 * kE; a.k_row = (int64_t)T * 3 * kE; a.k_head = kDh; a.v_off = kE;
         } else {
-            g.A = c->xb; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.N = kE; g.K = kE;  // Q rows only
-            g.Cb = c->qkv; g.ldcb = kE; g.Cf = nullptr;
-            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
             a.Q = c->qkv; a.q_row = (int64_t)T * kE; a.q_tok = kE;
-            a.K = cache_l; a.k_tok = s.N * kKvRow; a.k_row = kKvRow; a.k_head = 0; a.v_off = kDh;
+            a.K = s.kv + (size_t)l * T * s.N * kKvRow; a.k_tok = s.N * kKvRow; a.k_row = kKvRow; a.k_head = 0; a.v_off = kDh;
         }
         if (int rc = item_attention(c, a, T, st)) return rc;
-        g.A = c->ob; g.W = wb + o.item_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;
-        g.Cb = c->xb; g.ldcb = kE; g.Cf = c->xf; g.ldcf = kE;
-        if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
-
-        // ---- MLP ------------------------------------------------------------------------------------------
-        g.A = c->xb; g.W = wb + o.mlp_w1 + (size_t)l * kHid * kE; g.N = kHid; g.K = kE;
-        g.Cb = c->hb; g.ldcb = kHid; g.Cf = nullptr; g.bias = nullptr;
-        if (int rc = gemm<EPI_BIAS_GELU_BF16>(c, g, st)) return rc;
-        g.A = c->hb; g.lda = kHid; g.W = wb + o.mlp_w2 + (size_t)l * kE * kHid; g.N = kE; g.K = kHid;
-        g.Cb = c->xb; g.ldcb = kE; g.Cf = c->xf; g.ldcf = kE;
-        if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+        for (int64_t r0 = 0; r0 < R; r0 += sub_rows) {
+            const int64_t nr = std::min(sub_rows, R - r0);
+            if (int rc = second_half(l, r0, nr)) return rc;
+            if (l + 1 < L)
+                if (int rc = first_half(l + 1, r0, nr)) return rc;
+        }
     }
     c->last_rows = R;
     c->last_T = T;
@@ -388,6 +414,7 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "gemm_impl")) { c->gemm_impl = (int)value; return 0; }
     if (!strcmp(key, "chunk_rows")) { c->cfg.chunk_rows = (int)value; return 0; }
     if (!strcmp(key, "time_kernels")) { c->time_kernels = (int)value; return 0; }
+    if (!strcmp(key, "sub_tokens")) { c->sub_tok_opt = value; return 0; }
     last_error() = std::string("unknown option ") + key;
     return 2;
 }

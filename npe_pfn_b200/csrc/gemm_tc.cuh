@@ -26,7 +26,9 @@ constexpr int GT_BM = 128, GT_BN = 192, GT_BK = 64, GT_STAGES = 4, GT_THREADS = 
 constexpr int GT_A_BYTES = GT_BM * GT_BK * 2;   // 16 KB
 constexpr int GT_B_BYTES = GT_BN * GT_BK * 2;   // 24 KB
 constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
-constexpr int GT_SMEM_BYTES = 1024 + GT_STAGES * GT_STAGE_BYTES + 256;
+constexpr int GT_EPI_WARPS = 8;
+constexpr int GT_STAGING_BYTES = 8192;          // per epilogue warp: two 4 KB sub-tile buffers
+constexpr int GT_SMEM_BYTES = 1024 + GT_STAGES * GT_STAGE_BYTES + GT_EPI_WARPS * GT_STAGING_BYTES + 512;
 constexpr int GT_TMEM_COLS = 512, GT_ACC_STRIDE = 256;
 
 struct GemmTcArgs {
@@ -74,22 +76,60 @@ __device__ __forceinline__ float gelu_fast(float x) {
     return 0.5f * x * (1.0f + erf);
 }
 
+// ---- epilogue: every global access goes through TMA on 32 x 32 sub-tiles staged in swizzled shared memory ----------
+// (direct per-thread row accesses touch 32 different lines per warp instruction and saturate the LSU: r1 profile)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
+// sub-tile layouts: fp32 [32 rows][128 B] with the 128-byte swizzle, bf16 [32 rows][64 B] with the 64-byte swizzle
+__device__ __forceinline__ uint32_t sw128_off(int row, int q) { return (uint32_t)(row * 128 + ((q ^ (row & 7)) << 4)); }
+__device__ __forceinline__ uint32_t sw64_off(int row, int q) { return (uint32_t)(row * 64 + ((q ^ ((row >> 1) & 3)) << 4)); }
+
+struct EpiMaps {
+    const CUtensorMap* cb;  // bf16 output, box 32 x 32, SWIZZLE_64B
+    const CUtensorMap* cf;  // fp32 output / residual, box 32 x 32, SWIZZLE_128B
+};
+
+// One warp, one 128 x 192 accumulator tile: rows [row0, row0 + 32) of the tile (row0 already includes the warp's
+// lane quarter).  `stage` = this warp's 8 KB staging area, `rbar` = its two residual mbarriers, `ruse` = use counters.
 template <int EPI>
-__device__ __forceinline__ void gemm_tc_epilogue(const GemmTcArgs& p, uint32_t tacc, int64_t row, int n0) {
-    const bool row_ok = row < p.M;
+__device__ __forceinline__ void gemm_tc_epilogue(const GemmTcArgs& p, const EpiMaps& mp, uint32_t tacc, int row0, int n0,
+                                                 uint32_t stage, uint32_t rbar, uint32_t (&ruse)[2], int lane) {
+    constexpr int NCH = GT_BN / 32;
     if (EPI == EPI_RESID_LN) {
-        // N == 192: the thread owns a complete row.  Pass 1: x = acc + residual, sums, x parked back in TMEM.
-        float* xr = p.Cf + row * p.ldcf;
+        // pass 1: x = acc + residual (fp32 residual slices arrive by TMA, double-buffered), row sums, x parked in TMEM
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll 1
-        for (int c = 0; c < GT_BN / 32; ++c) {
-            uint32_t v[32];
+        for (int c = 0; c < NCH; ++c) {
             __syncwarp();
+            if (lane == 0 && c + 1 < NCH) {
+                const uint32_t b = (uint32_t)(c + 1) & 1u;
+                mbar_expect_tx(rbar + 8 * b, 4096);
+                tma_load_2d(stage + b * 4096, mp.cf, rbar + 8 * b, (c + 1) * 32, row0);
+            }
+            uint32_t v[32];
             tmem_ld32(tacc + c * 32, v);
             tmem_wait_ld();
+            const uint32_t b = (uint32_t)c & 1u;
+            mbar_wait(rbar + 8 * b, ruse[b] & 1u);
+            ruse[b]++;
+            const uint32_t rb = stage + b * 4096;
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
-                float4 r4 = row_ok ? *reinterpret_cast<const float4*>(xr + c * 32 + 4 * q) : make_float4(0.f, 0.f, 0.f, 0.f);
+                const float4 r4 = lds128(rb + sw128_off(lane, q));
                 const float x0 = __uint_as_float(v[4 * q + 0]) + r4.x, x1 = __uint_as_float(v[4 * q + 1]) + r4.y;
                 const float x2 = __uint_as_float(v[4 * q + 2]) + r4.z, x3 = __uint_as_float(v[4 * q + 3]) + r4.w;
                 s1 += (x0 + x1) + (x2 + x3);
@@ -103,58 +143,67 @@ __device__ __forceinline__ void gemm_tc_epilogue(const GemmTcArgs& p, uint32_t t
         const float mu = s1 * (1.0f / kE);
         const float var = fmaxf(s2 * (1.0f / kE) - mu * mu, 0.f);
         const float rs = rsqrtf(var + p.ln_eps);
-        bf16* br = p.Cb + row * p.ldcb;
+        // pass 2: normalise; fp32 sub-tile -> buffer 0, bf16 sub-tile -> buffer 1, both stored by TMA
 #pragma unroll 1
-        for (int c = 0; c < GT_BN / 32; ++c) {
+        for (int c = 0; c < NCH; ++c) {
             uint32_t v[32];
             __syncwarp();
             tmem_ld32(tacc + c * 32, v);
             tmem_wait_ld();
-            if (row_ok) {
+            if (lane == 0) bulk_wait_read0();  // the previous sub-tile stores have finished reading the buffers
+            __syncwarp();
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    float y[8];
+            for (int q = 0; q < 4; ++q) {
+                float y[8];
 #pragma unroll
-                    for (int i = 0; i < 8; ++i) y[i] = (__uint_as_float(v[8 * q + i]) - mu) * rs;
-                    *reinterpret_cast<float4*>(xr + c * 32 + 8 * q) = make_float4(y[0], y[1], y[2], y[3]);
-                    *reinterpret_cast<float4*>(xr + c * 32 + 8 * q + 4) = make_float4(y[4], y[5], y[6], y[7]);
-                    uint4 o;
-                    o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-                    o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-                    *reinterpret_cast<uint4*>(br + c * 32 + 8 * q) = o;
-                }
+                for (int i = 0; i < 8; ++i) y[i] = (__uint_as_float(v[8 * q + i]) - mu) * rs;
+                sts128(stage + sw128_off(lane, 2 * q), __float_as_uint(y[0]), __float_as_uint(y[1]), __float_as_uint(y[2]),
+                       __float_as_uint(y[3]));
+                sts128(stage + sw128_off(lane, 2 * q + 1), __float_as_uint(y[4]), __float_as_uint(y[5]),
+                       __float_as_uint(y[6]), __float_as_uint(y[7]));
+                sts128(stage + 4096 + sw64_off(lane, q), pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]),
+                       pack_bf16x2(y[4], y[5]), pack_bf16x2(y[6], y[7]));
+            }
+            fence_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                tma_store_2d(mp.cf, stage, c * 32, row0);
+                tma_store_2d(mp.cb, stage + 4096, c * 32, row0);
+                bulk_commit();
             }
         }
         return;
     }
 #pragma unroll 1
-    for (int c = 0; c < GT_BN / 32; ++c) {
+    for (int c = 0; c < NCH; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= p.N) break;  // warp-uniform
         uint32_t v[32];
         __syncwarp();
         tmem_ld32(tacc + c * 32, v);
         tmem_wait_ld();
-        const int col0 = n0 + c * 32;
-        const bool live = row_ok && col0 < p.N;  // the TMEM load above stays warp-uniform; only stores are guarded
-        if (live && EPI == EPI_BIAS_SCALE_F32) {
-            float* dst = p.Cf + row * p.ldcf + col0;
+        const uint32_t buf = stage + (uint32_t)(c & 1) * 4096;  // alternate buffers: only wait for the store before last
+        // two staging buffers alternate: before rewriting one, all stores but the most recent have read their source
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+        if (EPI == EPI_BIAS_SCALE_F32) {
 #pragma unroll
             for (int q = 0; q < 8; ++q) {
                 const int col = col0 + 4 * q;
+                float b[4] = {0.f, 0.f, 0.f, 0.f};
                 if (col + 3 < p.N) {
                     const float4 b4 = *reinterpret_cast<const float4*>(p.bias + col);
-                    float4 o;
-                    o.x = (__uint_as_float(v[4 * q + 0]) + b4.x) * p.scale;
-                    o.y = (__uint_as_float(v[4 * q + 1]) + b4.y) * p.scale;
-                    o.z = (__uint_as_float(v[4 * q + 2]) + b4.z) * p.scale;
-                    o.w = (__uint_as_float(v[4 * q + 3]) + b4.w) * p.scale;
-                    *reinterpret_cast<float4*>(dst + 4 * q) = o;
+                    b[0] = b4.x; b[1] = b4.y; b[2] = b4.z; b[3] = b4.w;
                 } else {
                     for (int i = 0; i < 4; ++i)
-                        if (col + i < p.N) dst[4 * q + i] = (__uint_as_float(v[4 * q + i]) + p.bias[col + i]) * p.scale;
+                        if (col + i < p.N) b[i] = p.bias[col + i];
                 }
+                sts128(buf + sw128_off(lane, q), __float_as_uint((__uint_as_float(v[4 * q + 0]) + b[0]) * p.scale),
+                       __float_as_uint((__uint_as_float(v[4 * q + 1]) + b[1]) * p.scale),
+                       __float_as_uint((__uint_as_float(v[4 * q + 2]) + b[2]) * p.scale),
+                       __float_as_uint((__uint_as_float(v[4 * q + 3]) + b[3]) * p.scale));
             }
-        } else if (live) {
-            bf16* dst = p.Cb + row * p.ldcb + col0;
+        } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 float y[8];
@@ -170,27 +219,34 @@ __device__ __forceinline__ void gemm_tc_epilogue(const GemmTcArgs& p, uint32_t t
 #pragma unroll
                     for (int i = 0; i < 8; ++i) y[i] = gelu_fast(y[i]);
                 }
-                uint4 o;
-                o.x = pack_bf16x2(y[0], y[1]); o.y = pack_bf16x2(y[2], y[3]);
-                o.z = pack_bf16x2(y[4], y[5]); o.w = pack_bf16x2(y[6], y[7]);
-                *reinterpret_cast<uint4*>(dst + 8 * q) = o;
+                sts128(buf + sw64_off(lane, q), pack_bf16x2(y[0], y[1]), pack_bf16x2(y[2], y[3]), pack_bf16x2(y[4], y[5]),
+                       pack_bf16x2(y[6], y[7]));
             }
+        }
+        fence_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(EPI == EPI_BIAS_SCALE_F32 ? mp.cf : mp.cb, buf, col0, row0);
+            bulk_commit();
         }
     }
 }
 
 template <int EPI>
 __global__ void __launch_bounds__(GT_THREADS, 1)
-gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const GemmTcArgs p) {
+gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+               const __grid_constant__ CUtensorMap tmCb, const __grid_constant__ CUtensorMap tmCf, const GemmTcArgs p) {
     extern __shared__ uint8_t gt_smem_raw[];
     const uint32_t raw = smem_u32(gt_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t bars = base + GT_STAGES * GT_STAGE_BYTES;
+    const uint32_t staging = base + GT_STAGES * GT_STAGE_BYTES;                 // 8 epilogue warps x 8 KB
+    const uint32_t bars = staging + GT_EPI_WARPS * GT_STAGING_BYTES;
     const uint32_t bar_full = bars;                      // [GT_STAGES]
     const uint32_t bar_empty = bars + 8 * GT_STAGES;     // [GT_STAGES]
     const uint32_t bar_acc_full = bars + 16 * GT_STAGES;   // [2]
     const uint32_t bar_acc_empty = bar_acc_full + 16;      // [2]
-    const uint32_t tmem_slot = bar_acc_full + 32;
+    const uint32_t bar_resid = bar_acc_full + 32;          // [GT_EPI_WARPS][2] residual sub-tiles landed
+    const uint32_t tmem_slot = bar_resid + 16 * GT_EPI_WARPS;
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(gt_smem_raw + (tmem_slot - raw));
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kblocks = p.K / GT_BK;
@@ -204,6 +260,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_init(bar_acc_full + 8 * b, 1);
             mbar_init(bar_acc_empty + 8 * b, 128);
         }
+        for (int w = 0; w < 2 * GT_EPI_WARPS; ++w) mbar_init(bar_resid + 8 * w, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 9) {
@@ -262,17 +319,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // ================= epilogue warpgroups =================
         const uint32_t e = (uint32_t)warp >> 2;  // warpgroup 0 / 1 <-> accumulator 0 / 1
         const uint32_t lane_base = (uint32_t)(warp & 3) * 32u;
+        const uint32_t stage = staging + (uint32_t)warp * GT_STAGING_BYTES;
+        const uint32_t rbar = bar_resid + 16 * (uint32_t)warp;
+        const EpiMaps mp{&tmCb, &tmCf};
+        uint32_t ruse[2] = {0u, 0u};
         uint32_t lt = 0;
         for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++lt) {
             if ((lt & 1u) != e) continue;
             const int m_blk = (int)(tile / p.n_chunks), n_blk = (int)(tile % p.n_chunks);
+            const int row0 = m_blk * GT_BM + (int)lane_base;
+            if (EPI == EPI_RESID_LN && lane == 0) {
+                bulk_wait_read0();  // the previous tile's stores no longer read the staging buffers
+                mbar_expect_tx(rbar, 4096);
+                tma_load_2d(stage, &tmCf, rbar, 0, row0);  // first residual slice: overlaps the accumulator wait
+            }
             mbar_wait(bar_acc_full + 8 * e, (lt >> 1) & 1u);
             tc_fence_after();
             const uint32_t tacc = tmem + (lane_base << 16) + e * GT_ACC_STRIDE;
-            gemm_tc_epilogue<EPI>(p, tacc, (int64_t)m_blk * GT_BM + lane_base + lane, n_blk * GT_BN);
+            gemm_tc_epilogue<EPI>(p, mp, tacc, row0, n_blk * GT_BN, stage, rbar, ruse, lane);
             tc_fence_before();
             mbar_arrive(bar_acc_empty + 8 * e);
         }
+        if (lane == 0) bulk_wait0();  // all TMA stores of this warp have completed before the CTA exits
     }
     tc_fence_before();
     __syncthreads();
@@ -296,6 +364,20 @@ static inline bool make_map2_sw128(CUtensorMap* m, const void* base, uint64_t in
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
+// 2-D output / residual map over a row-major matrix, box = 32 columns x 32 rows
+static inline bool make_map2_out(CUtensorMap* m, const void* base, bool fp32, uint64_t cols, uint64_t rows,
+                                 uint64_t row_bytes) {
+    PFN_encodeTiled fn = get_encode_fn();
+    if (!fn) return false;
+    cuuint64_t dims[2] = {cols, rows};
+    cuuint64_t strides[1] = {row_bytes};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, fp32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+              strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, fp32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 template <int EPI>
 static inline cudaError_t launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st) {
     static bool configured = false;
@@ -305,16 +387,23 @@ static inline cudaError_t launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStr
         configured = true;
     }
     if (a.K % GT_BK != 0 || (EPI == EPI_RESID_LN && a.N != GT_BN)) return cudaErrorInvalidValue;
-    CUtensorMap mA, mW;
+    CUtensorMap mA, mW, mCb, mCf;
     if (!make_map2_sw128(&mA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, GT_BM)) return cudaErrorInvalidValue;
     if (!make_map2_sw128(&mW, a.W, (uint64_t)a.K, (uint64_t)a.N, (uint64_t)a.K * 2, GT_BN)) return cudaErrorInvalidValue;
+    const bool need_b = EPI != EPI_BIAS_SCALE_F32, need_f = EPI == EPI_BIAS_SCALE_F32 || EPI == EPI_RESID_LN;
+    if (need_b && !make_map2_out(&mCb, a.Cb, false, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldcb * 2))
+        return cudaErrorInvalidValue;
+    if (need_f && !make_map2_out(&mCf, a.Cf, true, (uint64_t)a.N, (uint64_t)a.M, (uint64_t)a.ldcf * 4))
+        return cudaErrorInvalidValue;
+    if (!need_b) mCb = mCf;
+    if (!need_f) mCf = mCb;
     GemmTcArgs p{};
     p.M = a.M; p.N = a.N; p.K = a.K; p.Cb = a.Cb; p.ldcb = a.ldcb; p.Cf = a.Cf; p.ldcf = a.ldcf; p.bias = a.bias;
     p.scale = a.scale; p.ln_eps = a.ln_eps;
     p.n_chunks = (a.N + GT_BN - 1) / GT_BN;
     p.tiles = ceil_div(a.M, GT_BM) * p.n_chunks;
     const unsigned grid = (unsigned)std::min<int64_t>(p.tiles, num_sms);
-    gemm_tc_kernel<EPI><<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(mA, mW, p);
+    gemm_tc_kernel<EPI><<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(mA, mW, mCb, mCf, p);
     return cudaGetLastError();
 }
 

@@ -304,18 +304,19 @@ __global__ void __launch_bounds__(FAM_WARPS * 32) feature_attn_mma_kernel(const 
     }
 }
 
-// head-0 K/V of the context rows -> cache [T][N][64] (K 0..31 | V 32..63) for one layer
-__global__ void kv_cache_kernel(const bf16* __restrict__ qkv, int64_t N, int T, bf16* __restrict__ cache) {
+// head-0 K/V of context rows [r0, r0 + nr) -> cache [T][N][64] (K 0..31 | V 32..63) for one layer
+__global__ void kv_cache_kernel(const bf16* __restrict__ qkv, int64_t nr, int T, int64_t r0, int64_t N,
+                                bf16* __restrict__ cache) {
     // one thread per 16 bytes: (n, t, part in 0..7): parts 0-3 = K, 4-7 = V
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t total = N * T * 8;
+    const int64_t total = nr * T * 8;
     if (idx >= total) return;
     const int part = (int)(idx & 7);
     const int64_t nt = idx >> 3;
     const int t = (int)(nt % T);
     const int64_t n = nt / T;
     const bf16* src = qkv + (n * T + t) * 3 * kE + (part < 4 ? kE + part * 8 : 2 * kE + (part - 4) * 8);
-    bf16* dst = cache + ((int64_t)t * N + n) * kKvRow + part * 8;
+    bf16* dst = cache + ((int64_t)t * N + r0 + n) * kKvRow + part * 8;
     *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
 }
 
