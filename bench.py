@@ -181,6 +181,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--attn", default=None, choices=[None, "mma", "tc"])
     ap.add_argument("--gemm", default=None, choices=[None, "mma", "tc"])
+    ap.add_argument("--attn-poly", type=int, default=None)
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -209,6 +210,8 @@ def main():
         eng.set_option("attn_impl", 1 if args.attn == "tc" else 0)
     if args.gemm:
         eng.set_option("gemm_impl", 1 if args.gemm == "tc" else 0)
+    if args.attn_poly is not None:
+        eng.set_option("attn_poly", args.attn_poly)
     post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"engine": eng})
     post.rank_row_offset = rank << 40
     post.append_simulations(theta_p, x_p)

@@ -121,6 +121,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// exp2 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
+// polynomial for 2^f (max relative error 7.7e-5, P is rounded to bf16 = 3.9e-3 anyway), exponent re-inserted
+// with one integer shift-add.  Used for a fraction of the elements so MUFU and FMA pipes work in parallel.
+__device__ __forceinline__ float exp2_poly(float x) {
+    x = fmaxf(x, -126.0f);
+    const float t = __fadd_rn(x, 12582912.0f);  // 1.5 * 2^23: the low mantissa bits now hold round(x)
+    const float f = __fsub_rn(x, __fsub_rn(t, 12582912.0f));
+    float p = __fmaf_rn(0.05508868396282196f, f, 0.24260404706001282f);
+    p = __fmaf_rn(p, f, 0.6932762265205383f);
+    p = __fmaf_rn(p, f, 0.9999289512634277f);
+    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+}
+
+// POLY_MOD = 0: every exponential on MUFU; k > 0: one pair of every k pairs uses exp2_poly
+template <int POLY_MOD>
 __global__ void __launch_bounds__(TC_THREADS, 2)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs p) {
     extern __shared__ uint8_t tc_smem_raw[];
@@ -284,8 +299,11 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
                 const int cc = i >> 4, ii = (2 * i) & 31;
-                const float p0 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii]), sc, -m_ref));
-                const float p1 = fast_exp2(fmaf(__uint_as_float(sv[cc][ii + 1]), sc, -m_ref));
+                const float x0 = fmaf(__uint_as_float(sv[cc][ii]), sc, -m_ref);
+                const float x1 = fmaf(__uint_as_float(sv[cc][ii + 1]), sc, -m_ref);
+                const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
+                const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
+                const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
                 l0 += p0;
                 l1 += p1;
                 pk[i] = pack_bf16x2(p0, p1);
@@ -355,13 +373,21 @@ static inline bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, cudaStream_t st) {
+template <int POLY_MOD>
+static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUtensorMap& mkv, const TcArgs& p, dim3 grid,
+                                              cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TC_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<POLY_MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    attn_tc_kernel<POLY_MOD><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
+    return cudaGetLastError();
+}
+
+static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, int poly_mod, cudaStream_t st) {
     CUtensorMap mq, mkv;
     TcArgs p{};
     p.O = a.O; p.o_row = a.o_row; p.o_tok = a.o_tok; p.R = a.R; p.N = a.N;
@@ -384,8 +410,15 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, cu
         p.kv_ctx_mode = 0; p.kx0 = 0; p.kx_head = 0; p.v_dx = a.v_off;
     }
     dim3 grid((unsigned)ceil_div(a.R, TC_BM), (unsigned)heads, (unsigned)T);
-    attn_tc_kernel<<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
-    return cudaGetLastError();
+    switch (poly_mod) {
+        case 0: return launch_attn_tc_impl<0>(mq, mkv, p, grid, st);
+        case 2: return launch_attn_tc_impl<2>(mq, mkv, p, grid, st);
+        case 3: return launch_attn_tc_impl<3>(mq, mkv, p, grid, st);
+        case 4: return launch_attn_tc_impl<4>(mq, mkv, p, grid, st);
+        case 6: return launch_attn_tc_impl<6>(mq, mkv, p, grid, st);
+        case 8: return launch_attn_tc_impl<8>(mq, mkv, p, grid, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 }  // namespace pfn

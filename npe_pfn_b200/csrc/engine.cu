@@ -82,6 +82,7 @@ struct pfn_ctx {
     int last_T = 0;
     int attn_impl = 1;  // 0 = mma.sync, 1 = tcgen05
     int gemm_impl = 1;  // 0 = mma.sync, 1 = tcgen05
+    int attn_poly = 0;  // one pair of every k pairs of exponentials on the FMA pipes (0 = all on MUFU; r1 sweep: no gain)
     int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
     int time_kernels = 0;
@@ -185,7 +186,7 @@ int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
     TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
 #ifdef PFN_WITH_ATTN_TC
     if (c->attn_impl == 1) {
-        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, st));
+        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly, st));
     } else
 #endif
     {
@@ -412,6 +413,11 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     PFN_REQUIRE(c && key, "null argument");
     if (!strcmp(key, "attn_impl")) { c->attn_impl = (int)value; return 0; }
     if (!strcmp(key, "gemm_impl")) { c->gemm_impl = (int)value; return 0; }
+    if (!strcmp(key, "attn_poly")) {
+        PFN_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4 || value == 6 || value == 8, "attn_poly must be 0,2,3,4,6,8");
+        c->attn_poly = (int)value;
+        return 0;
+    }
     if (!strcmp(key, "chunk_rows")) { c->cfg.chunk_rows = (int)value; return 0; }
     if (!strcmp(key, "time_kernels")) { c->time_kernels = (int)value; return 0; }
     if (!strcmp(key, "sub_tokens")) { c->sub_tok_opt = value; return 0; }

@@ -15,7 +15,7 @@ bookkeeping stay on the GPU; results are returned as CPU tensors like the refere
 """
 from __future__ import annotations
 
-import math
+import itertools
 from typing import Literal, Mapping, Optional
 
 import torch
@@ -26,6 +26,9 @@ from .accept_reject_sampler import accept_reject_sample
 from .estimator import B200TabPFNRegressor, draw_seed
 from .support_posterior import get_filtering_method
 from .utils import box_bounds_of
+
+
+_UID = itertools.count(1)  # identifies a posterior object in the engine's slot tags (id() can be reused after gc)
 
 
 class _Context:
@@ -60,6 +63,7 @@ class NPE_PFN_Core:
         self.x_shape = x_shape
         self._theta_train = None
         self._x_train = None
+        self._uid = next(_UID)
         self._ctx_version = 0
         self._ctx: Optional[_Context] = None
         self._prior_bounds = "unset"
@@ -76,6 +80,7 @@ class NPE_PFN_Core:
 
     def __setstate__(self, state):
         self.__dict__.update(state)
+        self._uid = next(_UID)
         self._model = B200TabPFNRegressor(**self.regressor_init_kwargs)
 
     # -- data -----------------------------------------------------------------------------------------
@@ -137,7 +142,7 @@ class NPE_PFN_Core:
         """Slot holding the K/V cache of (ctx, d); prefilled on first use, shared engine slots are tagged."""
         eng = self.engine
         slot = d % eng.max_slots
-        tag = (id(self), ctx.key, d)
+        tag = (self._uid, ctx.key, d)
         tags = eng.__dict__.setdefault("_slot_tags", {})
         if tags.get(slot) != tag:
             eng.prefill_joint(slot, ctx.joint, ctx.dim_x + d)

@@ -193,6 +193,23 @@ def test_log_prob_vs_reference_loop(engine, weights):
     assert torch.allclose(lp, lp_chunked, atol=1e-5)
 
 
+def test_slot_cache_not_shared_between_posteriors(engine):
+    """Two posterior objects on one engine with different simulations must never reuse each other's K/V caches
+    (regression: slot tags once used id(self), which Python reuses after garbage collection)."""
+    from npe_pfn_b200 import NPE_PFN_Core
+    theta_a, x_a, g = _toy(60, 2, 2, 100)
+    theta_b, x_b, _ = _toy(60, 2, 2, 200)
+    th = torch.randn(16, 2, generator=g)
+    ref = {}
+    for name, (t, x) in {"a": (theta_a, x_a), "b": (theta_b, x_b)}.items():
+        ref[name] = NPE_PFN_Core(regressor_init_kwargs={"engine": engine}).append_simulations(t, x).log_prob(th, x[:1])
+    assert (ref["a"] - ref["b"]).abs().max() > 1e-3
+    for _ in range(3):  # interleave short-lived objects: same context version, possibly recycled ids
+        for name, (t, x) in {"a": (theta_a, x_a), "b": (theta_b, x_b)}.items():
+            lp = NPE_PFN_Core(regressor_init_kwargs={"engine": engine}).append_simulations(t, x).log_prob(th, x[:1])
+            assert torch.equal(lp, ref[name])
+
+
 def test_accept_compact_matches_torch(engine):
     g = torch.Generator().manual_seed(3)
     for M, dim in [(1, 2), (255, 3), (256, 1), (100_003, 5)]:
