@@ -12,7 +12,8 @@
 //              signalled with tcgen05.commit on mbarriers.
 // S is double-buffered in TMEM and the MMA thread runs one tile ahead (QK_{j+1} is issued before the softmax of
 // tile j finishes), so the exponential pipe (MUFU, the real bound at dh = 32: 128 FLOP per ex2) never waits
-// for the tensor pipe.  Two CTAs are resident per SM (256 TMEM columns each).
+// for the tensor pipe.  Three CTAs are resident per SM (128 + 32 TMEM columns each), so twelve softmax warps
+// keep the MUFU pipe busy through each other's TMEM-load / max / store / barrier phases.
 // r1 profile of the first version (single S buffer, 128-key tiles): profiles/r1_ncu_attn_tc_v1_metrics.txt.
 #pragma once
 #include <cuda.h>
@@ -22,13 +23,14 @@
 
 namespace pfn {
 
-constexpr int TC_BM = 128, TC_BN = 64, TC_STAGES = 8, TC_THREADS = 192;
+constexpr int TC_BM = 128, TC_BN = 64, TC_STAGES = 7, TC_THREADS = 192;
 constexpr int TC_Q_BYTES = TC_BM * kDh * 2;           // 8 KB: 128 rows x 64 B
 constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 4 KB: 64 keys x 64 B
 constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // K tile + V tile
-constexpr int TC_SMEM_BYTES = 1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256 + 16 * 1024;  // pad: 2 CTAs / SM
-constexpr int TC_TMEM_COLS = 256;                     // S0/P0: [0,64), S1/P1: [64,128), O: [128,160)
-constexpr int TC_COL_O = 128;
+// 66 816 B: three CTAs per SM fit in shared memory (200 KB), a fourth does not.  TMEM: each CTA takes 128 columns
+// (S0/P0 [0,64), S1/P1 [64,128)) plus a separate 32-column allocation for O: 3 x 160 = 480 of the 512 columns.
+constexpr int TC_SMEM_BYTES = 1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256;
+constexpr int TC_TMEM_COLS_S = 128, TC_TMEM_COLS_O = 32;
 
 struct TcArgs {
     bf16* O;
@@ -136,7 +138,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
 
 // POLY_MOD = 0: every exponential on MUFU; k > 0: one pair of every k pairs uses exp2_poly
 template <int POLY_MOD>
-__global__ void __launch_bounds__(TC_THREADS, 2)
+__global__ void __launch_bounds__(TC_THREADS, 3)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs p) {
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
@@ -152,7 +154,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t bar_p = bar_q + 24;                     // [2] P_j written into S buffer b       softmax -> MMA
     const uint32_t bar_pv = bar_q + 40;                    // O += P_j V_j finished (rescale guard) MMA -> softmax
     const uint32_t bar_o = bar_q + 48;                     // last O += P V finished
-    const uint32_t tmem_slot = bar_q + 56;
+    const uint32_t tmem_slot = bar_q + 56;                 // [2]: S/P columns, O columns
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(tc_smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -176,13 +178,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     }
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
-                     "r"((uint32_t)TC_TMEM_COLS) : "memory");
+                     "r"((uint32_t)TC_TMEM_COLS_S) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot + 4),
+                     "r"((uint32_t)TC_TMEM_COLS_O) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
-    const uint32_t tmem = *tmem_slot_ptr;
+    const uint32_t tmem = tmem_slot_ptr[0];     // S/P double buffer
+    const uint32_t tmem_o = tmem_slot_ptr[1];   // O accumulator
 
     if (warp == 4) {
         // ================= TMA producer =================
@@ -239,7 +244,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint32_t pa = tmem + (uint32_t)(b * TC_BN);
 #pragma unroll
                 for (int kk = 0; kk < TC_BN / 16; ++kk)  // 16 keys per step: 8 TMEM columns of P, 1 KB of V
-                    umma_ts(tmem + TC_COL_O, pa + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
+                    umma_ts(tmem_o, pa + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
                 tc_commit(bar_kv_empty + 8 * s);
                 tc_commit(bar_pv);
                 if (j + 2 < ntiles) issue_qk(j + 2);
@@ -249,6 +254,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     } else {
         // ================= softmax warps: thread = query row = TMEM lane =================
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
+        const uint32_t orow = tmem_o + ((uint32_t)(warp * 32) << 16);
         const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
         float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f;
         for (int j = 0; j < ntiles; ++j) {
@@ -256,23 +262,25 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const uint32_t scol = trow + (uint32_t)(b * TC_BN);
             mbar_wait(bar_s + 8 * b, (uint32_t)(j >> 1) & 1u);
             tc_fence_after();
-            uint32_t sv[2][32];
-            tmem_ld32(scol, sv[0]);
-            tmem_ld32(scol + 32, sv[1]);
+            // pass 1: both 32-column halves -> tile maximum (the second half is re-read later instead of being
+            // kept live, so the kernel fits the 112 registers that three CTAs per SM allow)
+            uint32_t sa[32], sb[32];
+            tmem_ld32(scol, sa);
+            tmem_ld32(scol + 32, sb);
             tmem_wait_ld();
             const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
             if (nvalid < TC_BN) {
 #pragma unroll
-                for (int c = 0; c < 2; ++c)
-#pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (c * 32 + i >= nvalid) sv[c][i] = 0xff800000u;  // -inf
+                for (int i = 0; i < 32; ++i) {
+                    if (i >= nvalid) sa[i] = 0xff800000u;  // -inf
+                    if (32 + i >= nvalid) sb[i] = 0xff800000u;
+                }
             }
             float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
             for (int i = 0; i < 32; ++i) {
-                mx0 = fmaxf(mx0, __uint_as_float(sv[0][i]));
-                mx1 = fmaxf(mx1, __uint_as_float(sv[1][i]));
+                mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
+                mx1 = fmaxf(mx1, __uint_as_float(sb[i]));
             }
             const float mt = fmaxf(mx0, mx1) * sc;
             if (j == 0) {
@@ -288,25 +296,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     mbar_wait(bar_pv, (uint32_t)(j - 1) & 1u);  // O += P_{j-1} V_{j-1} must have landed
                     tc_fence_after();
                     uint32_t ov[32];
-                    tmem_ld32(trow + TC_COL_O, ov);
+                    tmem_ld32(orow, ov);
                     tmem_wait_ld();
 #pragma unroll
                     for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                    tmem_st32(trow + TC_COL_O, ov);
+                    tmem_st32(orow, ov);
                 }
             }
+            // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs; first half from registers, second half re-read
             uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                const int cc = i >> 4, ii = (2 * i) & 31;
-                const float x0 = fmaf(__uint_as_float(sv[cc][ii]), sc, -m_ref);
-                const float x1 = fmaf(__uint_as_float(sv[cc][ii + 1]), sc, -m_ref);
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
+                const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
                 const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
                 const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
                 const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
                 l0 += p0;
                 l1 += p1;
                 pk[i] = pack_bf16x2(p0, p1);
+            }
+            tmem_ld32(scol + 32, sa);
+            tmem_wait_ld();
+            if (nvalid < TC_BN) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                    if (32 + i >= nvalid) sa[i] = 0xff800000u;
+            }
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
+                const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
+                const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
+                const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
+                const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
+                l0 += p0;
+                l1 += p1;
+                pk[16 + i] = pack_bf16x2(p0, p1);
             }
             tmem_st32(scol, pk);
             tmem_wait_st();
@@ -317,7 +343,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_wait(bar_o, 0);
         tc_fence_after();
         uint32_t ov[32];
-        tmem_ld32(trow + TC_COL_O, ov);
+        tmem_ld32(orow, ov);
         tmem_wait_ld();
         const int64_t r = m0 + warp * 32 + lane;
         if (r < p.R) {
@@ -337,7 +363,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_before();
     __syncthreads();
     if (warp == 5) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS)
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"((uint32_t)TC_TMEM_COLS_S)
+                     : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_o), "r"((uint32_t)TC_TMEM_COLS_O)
                      : "memory");
     }
 }
