@@ -61,12 +61,19 @@ def tokens(d):
 
 
 def flops_per_row(T, N):
-    """Algorithmic FLOPs of one test row x one dimension."""
-    return L * T * (28 * E * E + 4 * T * E + 4 * N * E) + 2 * E * HID + 2 * HID * BUCKETS
+    """Algorithmic FLOPs of one test row x one dimension as EXECUTED: SURVEY.md §8d's per-layer terms for layers
+    0..L-2; in the last layer only the y-token column goes through item attention, out-projections and the MLP
+    (the decoder reads nothing else), the feature-attention QKV / scores still cover all T tokens."""
+    full = T * (28 * E * E + 4 * T * E + 4 * N * E)
+    last = T * (12 * E * E + 4 * T * E) + (4 * E * E) + (4 * E * E + 4 * N * E) + 16 * E * E
+    return (L - 1) * full + last + 2 * E * HID + 2 * HID * BUCKETS
 
 
 def flops_prefill(T, N):
-    return L * (32 * N * T * E * E + 4 * N * T * T * E + 4 * T * N * N * E)
+    """Context rows: full layers 0..L-2; the last layer stops after its K/V projection (final states are unused)."""
+    full = 32 * N * T * E * E + 4 * N * T * T * E + 4 * T * N * N * E
+    last = N * T * (16 * E * E + 12 * E * E) + 4 * N * T * T * E
+    return (L - 1) * full + last
 
 
 def flops_per_step(S):

@@ -224,7 +224,13 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
     // its intermediates (feature-attention qkv, MLP hidden) live in small reused scratch buffers that stay in L2;
     // only the residual stream, the item queries and the attention output cross HBM once per layer.
     const int64_t sub_rows = c->sub_tok_opt > 0 ? std::max<int64_t>(1, std::min(c->sub_tok_opt, c->sub_tok) / T) : R;
+    // Dead-code elimination in the LAST layer: the decoder reads only the y-token (column T-1) of test rows, and
+    // nothing reads the final context states.  So for test rows the last layer's item attention, out-projection
+    // and MLP run on the y-token column alone (strided rows: leading dimension T*E), and for context rows the last
+    // layer stops after its K/V projection.  Identical results, ~1/12 * (T-1)/T less attention / MLP work.
+    const int64_t ycol = (int64_t)(T - 1) * kE;  // element offset of the y-token inside a row's token block
     auto first_half = [&](int l, int64_t r0, int64_t nr) -> int {  // feature attention + item-attention projections
+        const bool y_only = (l == L - 1) && !ctx_rows;
         const int64_t t0 = r0 * T, ntok = nr * T;
         GemmArgs g{};
         g.ln_eps = c->cfg.ln_eps;
@@ -242,10 +248,13 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
             }
             PFN_LAUNCH_OK(c);
         }
-        g.A = c->ob + t0 * kE; g.W = wb + o.feat_wo + (size_t)l * kE * kE; g.N = kE; g.K = kE;
-        g.Cb = c->xb + t0 * kE; g.ldcb = kE; g.Cf = c->xf + t0 * kE; g.ldcf = kE;
+        const int64_t off = y_only ? t0 * kE + ycol : t0 * kE;  // y_only: one row per test row, stride T*E
+        const int64_t ld = y_only ? (int64_t)T * kE : kE;
+        const int64_t rows = y_only ? nr : ntok;
+        g.A = c->ob + off; g.lda = ld; g.W = wb + o.feat_wo + (size_t)l * kE * kE; g.M = rows; g.N = kE; g.K = kE;
+        g.Cb = c->xb + off; g.ldcb = ld; g.Cf = c->xf + off; g.ldcf = ld;
         if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
-        g.A = c->xb + t0 * kE; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.K = kE; g.Cf = nullptr;
+        g.A = c->xb + off; g.lda = ld; g.W = wb + o.item_wqkv + (size_t)l * 3 * kE * kE; g.K = kE; g.Cf = nullptr;
         if (ctx_rows) {
             g.N = 3 * kE; g.Cb = c->qkv + t0 * 3 * kE; g.ldcb = 3 * kE;
             if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
@@ -253,40 +262,51 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
             kv_cache_kernel<<<(unsigned)ceil_div(ntok * 8, 256), 256, 0, st>>>(c->qkv + t0 * 3 * kE, nr, T, r0, s.N, cache_l);
             PFN_LAUNCH_OK(c);
         } else {
-            g.N = kE; g.Cb = c->qkv + t0 * kE; g.ldcb = kE;  // Q rows of the projection only
+            g.N = kE; g.Cb = c->qkv + off; g.ldcb = ld;  // Q rows of the projection only
             if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
         }
         return 0;
     };
     auto second_half = [&](int l, int64_t r0, int64_t nr) -> int {  // item out-projection + MLP
+        const bool y_only = (l == L - 1) && !ctx_rows;
         const int64_t t0 = r0 * T, ntok = nr * T;
+        const int64_t off = y_only ? t0 * kE + ycol : t0 * kE;
+        const int64_t ld = y_only ? (int64_t)T * kE : kE;
+        const int64_t rows = y_only ? nr : ntok;
         GemmArgs g{};
         g.ln_eps = c->cfg.ln_eps;
-        g.A = c->ob + t0 * kE; g.lda = kE; g.W = wb + o.item_wo + (size_t)l * kE * kE; g.M = ntok; g.N = kE; g.K = kE;
-        g.Cb = c->xb + t0 * kE; g.ldcb = kE; g.Cf = c->xf + t0 * kE; g.ldcf = kE;
+        g.A = c->ob + off; g.lda = ld; g.W = wb + o.item_wo + (size_t)l * kE * kE; g.M = rows; g.N = kE; g.K = kE;
+        g.Cb = c->xb + off; g.ldcb = ld; g.Cf = c->xf + off; g.ldcf = ld;
         if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
-        g.A = c->xb + t0 * kE; g.W = wb + o.mlp_w1 + (size_t)l * kHid * kE; g.N = kHid; g.K = kE;
+        g.A = c->xb + off; g.lda = ld; g.W = wb + o.mlp_w1 + (size_t)l * kHid * kE; g.N = kHid; g.K = kE;
         g.Cb = c->hb_s; g.ldcb = kHid; g.Cf = nullptr; g.bias = nullptr;
         if (int rc = gemm<EPI_BIAS_GELU_BF16>(c, g, st)) return rc;
         g.A = c->hb_s; g.lda = kHid; g.W = wb + o.mlp_w2 + (size_t)l * kE * kHid; g.N = kE; g.K = kHid;
-        g.Cb = c->xb + t0 * kE; g.ldcb = kE; g.Cf = c->xf + t0 * kE; g.ldcf = kE;
+        g.Cb = c->xb + off; g.ldcb = ld; g.Cf = c->xf + off; g.ldcf = ld;
         return gemm<EPI_RESID_LN>(c, g, st);
     };
 
     for (int64_t r0 = 0; r0 < R; r0 += sub_rows)
         if (int rc = first_half(0, r0, std::min(sub_rows, R - r0))) return rc;
     for (int l = 0; l < L; ++l) {
+        const bool last = l == L - 1;
+        if (last && ctx_rows) break;  // the context's last-layer K/V are cached; its final states are never read
         AttnArgs a{};
         a.R = R; a.N = s.N;
         a.O = c->ob; a.o_row = (int64_t)T * kE; a.o_tok = kE;
+        int Tq = T;  // token columns the queries cover
         if (ctx_rows) {
             a.Q = c->qkv; a.q_row = (int64_t)T * 3 * kE; a.q_tok = 3 * kE;
             a.K = c->qkv + kE; a.k_tok = 3 * kE; a.k_row = (int64_t)T * 3 * kE; a.k_head = kDh; a.v_off = kE;
         } else {
             a.Q = c->qkv; a.q_row = (int64_t)T * kE; a.q_tok = kE;
             a.K = s.kv + (size_t)l * T * s.N * kKvRow; a.k_tok = s.N * kKvRow; a.k_row = kKvRow; a.k_head = 0; a.v_off = kDh;
+            if (last) {  // y-token column only
+                a.Q += ycol; a.O += ycol; a.K += (int64_t)(T - 1) * s.N * kKvRow;
+                Tq = 1;
+            }
         }
-        if (int rc = item_attention(c, a, T, st)) return rc;
+        if (int rc = item_attention(c, a, Tq, st)) return rc;
         for (int64_t r0 = 0; r0 < R; r0 += sub_rows) {
             const int64_t nr = std::min(sub_rows, R - r0);
             if (int rc = second_half(l, r0, nr)) return rc;
