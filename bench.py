@@ -237,9 +237,10 @@ def main():
         return s
 
     def _all_gather(s):
-        out = [torch.empty_like(s) for _ in range(world)]
-        dist.all_gather(out, s)
-        return torch.cat(out, 0)
+        s = s.contiguous()  # the draws are a column slice of the joint test matrix
+        out = torch.empty((world * s.shape[0],) + tuple(s.shape[1:]), dtype=s.dtype, device=s.device)
+        dist.all_gather_into_tensor(out, s)
+        return out
 
     def step_e2e():
         """public API with host tensors: H2D of the simulations, sample(), D2H of the draws"""
