@@ -82,6 +82,7 @@ struct pfn_ctx {
     int last_T = 0;
     int attn_impl = 1;  // 0 = mma.sync, 1 = tcgen05
     int gemm_impl = 1;  // 0 = mma.sync, 1 = tcgen05
+    int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
     int attn_poly = 0;  // one pair of every k pairs of exponentials on the FMA pipes (0 = all on MUFU; r1 sweep: no gain)
     int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
@@ -433,6 +434,7 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     PFN_REQUIRE(c && key, "null argument");
     if (!strcmp(key, "attn_impl")) { c->attn_impl = (int)value; return 0; }
     if (!strcmp(key, "gemm_impl")) { c->gemm_impl = (int)value; return 0; }
+    if (!strcmp(key, "standardize_y")) { c->standardize_y = (int)value; return 0; }
     if (!strcmp(key, "attn_poly")) {
         PFN_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4 || value == 6 || value == 8, "attn_poly must be 0,2,3,4,6,8");
         c->attn_poly = (int)value;
@@ -464,7 +466,7 @@ int pfn_prefill(pfn_ctx* c, int slot, const float* X, int64_t ldx, const float* 
         PFN_CUDA_OK(cudaMalloc(&s.kv, need));
         s.kv_cap = need;
     }
-    fit_stats_kernel<<<2 * s.G + 1, 256, 0, st>>>(X, ldx, y, N, F, s.G, s.enc);
+    fit_stats_kernel<<<2 * s.G + 1, 256, 0, st>>>(X, ldx, y, N, F, s.G, s.enc, c->standardize_y);
     PFN_LAUNCH_OK(c);
     const int nb1 = c->cfg.num_buckets + 1;
     fit_finalize_kernel<<<(unsigned)ceil_div(std::max(nb1, s.G), 256), 256, 0, st>>>(s.enc, s.G, c->wf + c->off.borders,

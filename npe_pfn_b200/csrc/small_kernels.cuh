@@ -33,7 +33,7 @@ __device__ __forceinline__ double block_sum_double(double v, double* sh) {
 
 __global__ void __launch_bounds__(256) fit_stats_kernel(const float* __restrict__ X, int64_t ldx,
                                                         const float* __restrict__ y, int64_t N, int F, int G,
-                                                        float* __restrict__ enc) {
+                                                        float* __restrict__ enc, int standardize_y) {
     __shared__ double sh[8];
     const int c = blockIdx.x;
     const int Fp = 2 * G;
@@ -76,9 +76,10 @@ __global__ void __launch_bounds__(256) fit_stats_kernel(const float* __restrict_
     }
     q = block_sum_double(q, sh);
     const double std_d = N > 1 ? sqrt(q / (double)(N - 1)) : 0.0;
-    const float mean32 = (float)mean;
+    float mean32 = (float)mean;
     float std32 = (float)std_d;
     if (!isfinite(std32) || std32 == 0.f) std32 = 1.f;
+    if (!standardize_y) { mean32 = 0.f; std32 = 1.f; }  // classifier: class indices enter the y-encoder as they are
     double z = 0.0;
     for (int64_t i = threadIdx.x; i < N; i += blockDim.x) z += (double)((y[i] - mean32) / std32);
     z = block_sum_double(z, sh);

@@ -171,10 +171,12 @@ class Engine:
     def forward_logits(self, slot: int, X: torch.Tensor) -> torch.Tensor:
         X = _f32_rows(X, self.device)
         M = X.shape[0]
-        out = torch.empty(M, self.cfg.num_buckets, dtype=torch.float32, device=self.device)
+        B = self.cfg.num_buckets
+        ld = (B + 3) // 4 * 4  # the library wants 16-byte aligned logits rows
+        out = torch.empty(M, ld, dtype=torch.float32, device=self.device)
         self._check(self.lib.pfn_forward_logits(self._h, slot, _ptr(X), X.stride(0) if M > 1 else X.shape[1], M,
-                                                _ptr(out), out.stride(0), self._stream()))
-        return out
+                                                _ptr(out), ld, self._stream()))
+        return out if ld == B else out[:, :B]
 
     def head_sample(self, slot: int, logits: torch.Tensor, M: Optional[int] = None, uniforms=None, seed=0, row0=0,
                     offset=0, out_theta=None, ld_theta=1, with_log_prob=False, out_logp=None, eps=1e-15,

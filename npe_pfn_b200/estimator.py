@@ -89,3 +89,49 @@ class B200TabPFNRegressor:
         X = torch.as_tensor(X, dtype=torch.float32)
         logits = self.engine.forward_logits(self.slot, X)
         return {"criterion": B200Criterion(self.engine, self.slot, self.output_device), "logits": logits}
+
+
+_CLS_WEIGHTS = None
+
+
+def default_classifier_weights() -> PFNWeights:
+    """Seeded random init of the classifier architecture (no checkpoint offline), shared by engine and oracle."""
+    global _CLS_WEIGHTS
+    if _CLS_WEIGHTS is None:
+        from .weights import classifier_config
+        _CLS_WEIGHTS = PFNWeights.random_init(classifier_config())
+    return _CLS_WEIGHTS
+
+
+class B200TabPFNClassifier:
+    """`TabPFNClassifier(**kw).fit(X, y in {0..C-1})` / `.predict_proba(X) -> ndarray[m, C]` as the reference's
+    density-ratio wrapper uses it (`/root/reference/npe_pfn/npe_pfn.py:610, 661, 697`): the same per-feature
+    transformer with the classifier's own weights, class indices fed unscaled to the y-encoder, a 10-way decoder of
+    which the first `n_classes` logits are softmaxed (temperature 0.9).  Single estimator, identity preprocessing."""
+
+    def __init__(self, weights: Optional[PFNWeights] = None, device: Optional[int] = None,
+                 softmax_temperature: float = 0.9, n_estimators: int = 1, engine: Optional[Engine] = None, **_ignored):
+        if n_estimators != 1:
+            raise NotImplementedError("npe_pfn_b200 implements a single estimator with identity preprocessing")
+        if engine is None:
+            engine = get_engine(device=device, weights=weights or default_classifier_weights(),
+                                softmax_temperature=softmax_temperature, max_slots=1)
+            engine.set_option("standardize_y", 0)
+        self.engine = engine
+        self.n_classes = 0
+
+    def fit(self, X, y):
+        X = torch.as_tensor(X, dtype=torch.float32)
+        y = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
+        assert X.ndim == 2 and X.shape[0] == y.shape[0], "fit expects X[N, F], y[N]"
+        self.n_classes = int(y.max().item()) + 1
+        assert 2 <= self.n_classes <= self.engine.cfg.num_buckets
+        self.engine.prefill(0, X, y)
+        return self
+
+    def predict_proba(self, X):
+        if not self.n_classes:
+            raise RuntimeError("predict_proba called before fit")
+        X = torch.as_tensor(X, dtype=torch.float32)
+        logits = self.engine.forward_logits(0, X)[:, :self.n_classes]
+        return torch.softmax(logits, dim=-1).cpu().numpy()

@@ -16,6 +16,7 @@ bookkeeping stay on the GPU; results are returned as CPU tensors like the refere
 from __future__ import annotations
 
 import itertools
+import math
 from typing import Literal, Mapping, Optional
 
 import torch
@@ -23,7 +24,7 @@ from torch import Tensor
 from torch.distributions import Distribution
 
 from .accept_reject_sampler import accept_reject_sample
-from .estimator import B200TabPFNRegressor, draw_seed
+from .estimator import B200TabPFNClassifier, B200TabPFNRegressor, draw_seed
 from .support_posterior import get_filtering_method
 from .utils import box_bounds_of
 
@@ -368,10 +369,21 @@ class NPE_PFN_Core:
     def log_prob_batched(self, theta: Tensor, x: Tensor):
         raise NotImplementedError
 
-    def _ratio_based_log_prob(self, theta: Tensor, x: Tensor = None, **kwargs) -> Tensor:
-        raise NotImplementedError(
-            "ratio_based log_prob needs the TabPFN classifier head (npe_pfn.py:526-570, 603-704); it is listed as "
-            "the next row after the regressor path in DESIGN.md. Use mode='autoregressive'.")
+    def _ratio_based_log_prob(self, theta: Tensor, x: Tensor = None, num_posterior_samples: int = 5000,
+                              boundary_padding: float = 0.1, reuse_estimator_if_possible: bool = True,
+                              eps: float = 1e-15) -> Tensor:
+        """log p(theta | x) by density-ratio estimation (npe_pfn.py:526-570): a classifier separates posterior
+        draws from uniform draws on their padded bounding box; log p = log U + log(p1 + eps) - log(p0 + eps).
+        The classifier is re-fitted only when the observation, the context or the two parameters changed."""
+        if self._model_classifier is None:
+            self._model_classifier = DensityRatioWrapper(**self.classifier_init_kwargs)
+        theta_context, x_context = self.get_context(x)
+        wrapper = self._model_classifier
+        if not reuse_estimator_if_possible or wrapper.refit_necessary(x, x_context, theta_context,
+                                                                      num_posterior_samples, boundary_padding):
+            draws = self.sample(sample_shape=torch.Size([num_posterior_samples]), x=x)
+            wrapper.fit(x, draws, boundary_padding, x_context, theta_context)
+        return wrapper.ratio_log_probs(theta, eps)
 
     def _get_classifier_bounds(self):
         if self._model_classifier is None:
@@ -432,6 +444,57 @@ class _SupportCheck:
         k = int(count.item())  # the one host sync per rejection round (accept_reject_sampler.py:62)
         kept_lp = log_probs[idx[:k]] if log_probs is not None else None
         return rows[:k], kept_lp, k
+
+
+class DensityRatioWrapper:
+    """Posterior-vs-uniform classifier with a fit cache (npe_pfn.py:603-704).
+
+    `fit` draws as many uniform points on the padded bounding box of the posterior samples as there are samples,
+    labels them 0 / 1 and fits the classifier; `ratio_log_probs` turns its class probabilities into a log density
+    (points outside the box get the floor value log U + log(eps) - log(1 + eps))."""
+
+    def __init__(self, **init_kwargs):
+        self._classifier = B200TabPFNClassifier(**init_kwargs)
+        self._key = None  # (x, x_context, theta_context, n, padding) of the current fit
+        self._padded_dim_min = None
+        self._padded_dim_max = None
+        self._uniform_log_prob = None
+
+    def fit(self, x: Tensor, posterior_samples: Tensor, boundary_padding: float, x_context: Tensor,
+            theta_context: Tensor):
+        lo, hi = posterior_samples.min(dim=0).values, posterior_samples.max(dim=0).values
+        pad = boundary_padding * (hi - lo)
+        lo, hi = lo - pad, hi + pad
+        width = hi - lo
+        n = posterior_samples.shape[0]
+        uniform = torch.rand_like(posterior_samples) * width + lo
+        X = torch.cat([uniform, posterior_samples], dim=0)
+        y = torch.cat([torch.zeros(n), torch.ones(n)], dim=0)
+        self._key = (x, x_context, theta_context, n, boundary_padding)
+        self._padded_dim_min, self._padded_dim_max = lo, hi
+        self._uniform_log_prob = -torch.log(width).sum()
+        self._classifier.fit(X, y)
+
+    def refit_necessary(self, x: Tensor, x_context: Tensor, theta_context: Tensor, num_posterior_samples: int,
+                        boundary_padding: float) -> bool:
+        if self._key is None:
+            return True
+        x0, xc0, tc0, n0, pad0 = self._key
+
+        def same(a: Tensor, b: Tensor) -> bool:
+            return a.shape == b.shape and bool(torch.allclose(a, b))
+
+        return not (same(x, x0) and same(x_context, xc0) and same(theta_context, tc0)
+                    and num_posterior_samples == n0 and math.isclose(boundary_padding, pad0))
+
+    def ratio_log_probs(self, theta: Tensor, eps=1e-15) -> Tensor:
+        inside = ((theta >= self._padded_dim_min) & (theta <= self._padded_dim_max)).all(dim=1)
+        floor = self._uniform_log_prob + torch.log(torch.tensor(eps)) - torch.log(torch.tensor(1 + eps))
+        out = torch.full((theta.shape[0],), float(floor))
+        if inside.any():
+            probs = torch.as_tensor(self._classifier.predict_proba(theta[inside]))
+            out[inside] = self._uniform_log_prob + torch.log(probs[:, 1] + eps) - torch.log(probs[:, 0] + eps)
+        return out
 
 
 # NOTE: can never support batched sampling with filtering, as the context depends on x (npe_pfn.py:707)

@@ -202,10 +202,18 @@ class PFNWeights:
         return PFNWeights.random_init(cfg)
 
 
+def classifier_config() -> PFNConfig:
+    """TabPFNv2 classifier: the same transformer with its own weights and a 10-way decoder (max_num_classes = 10,
+    SURVEY.md Appendix A.1); its `borders` are unused."""
+    return PFNConfig(num_buckets=10, seed=1)
+
+
 def default_borders(num_buckets: int) -> torch.Tensor:
     """Bucket borders for the random-init model: standard-normal quantiles on an
     even probability grid (upstream derives its borders from prior-data
     quantiles)."""
+    if num_buckets < 100:  # classifier head: placeholder grid
+        return torch.linspace(-1.0, 1.0, num_buckets + 1, dtype=torch.float32)
     p = torch.linspace(2e-4, 1.0 - 2e-4, num_buckets + 1, dtype=torch.float64)
     b = torch.distributions.Normal(0.0, 1.0).icdf(p)
     b = b.float()

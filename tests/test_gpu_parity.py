@@ -373,6 +373,53 @@ def test_five_call_protocol(engine, weights):
     assert nll.shape == (9,) and torch.isfinite(nll).all()
 
 
+def test_classifier_and_ratio_log_prob(engine, weights):
+    """TabPFN classifier head (npe_pfn.py:610, 661, 697) and the ratio-based log-prob built on it (:526-570)."""
+    from npe_pfn_b200 import BoxUniform, TabPFN_Based_NPE_PFN
+    from npe_pfn_b200.estimator import B200TabPFNClassifier, default_classifier_weights
+    from oracle.classifier import OracleTabPFNClassifier
+    g = torch.Generator().manual_seed(8)
+    n, d = 150, 3
+    X = torch.cat([torch.rand(n, d, generator=g) * 4 - 2, torch.randn(n, d, generator=g) * 0.5], 0)
+    y = torch.cat([torch.zeros(n), torch.ones(n)])
+    Xt = torch.randn(64, d, generator=g)
+    got = B200TabPFNClassifier().fit(X, y).predict_proba(Xt)
+    ref = OracleTabPFNClassifier(weights=default_classifier_weights()).fit(X, y).predict_proba(Xt)
+    assert got.shape == (64, 2) and abs(got.sum(1) - 1).max() < 1e-5
+    print("classifier max |dp| =", abs(got - ref).max())
+    assert abs(got - ref).max() <= 0.02
+    # ratio-based log-prob through the posterior object: finite, cached classifier is reused, bounds exposed
+    theta, x, _ = _toy(80, 2, 2, 3)
+    prior = BoxUniform(-4 * torch.ones(2), 4 * torch.ones(2))
+    post = TabPFN_Based_NPE_PFN(prior=prior, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    th = torch.randn(40, 2, generator=g)
+    th[0] = 100.0  # outside the classifier's box -> floor value
+    lp1 = post.log_prob(th, x[:1], mode="ratio_based", num_posterior_samples=200)
+    assert lp1.shape == (40,) and torch.isfinite(lp1).all()
+    lo, hi = post._get_classifier_bounds()
+    assert lo.shape == (2,) and bool((hi > lo).all())
+    wrapper = post._model_classifier
+    assert not wrapper.refit_necessary(x[:1], *reversed(post.get_context(x[:1])), 200, 0.1)
+    lp2 = post.log_prob(th, x[:1], mode="ratio_based", num_posterior_samples=200)
+    assert torch.equal(lp1, lp2)  # same fitted classifier, deterministic prediction
+    floor = float(wrapper._uniform_log_prob + math.log(1e-15) - math.log(1 + 1e-15))
+    assert abs(float(lp1[0]) - floor) < 1e-3 and float(lp1.min()) >= floor - 1e-3  # outside the box -> floor value
+    assert wrapper.refit_necessary(x[1:2], *reversed(post.get_context(x[1:2])), 200, 0.1)
+
+
+def test_tsnpe_rounds_ratio_based(engine):
+    """run_tsnpe_pfn with its default log_prob_mode ("ratio_based", tsnpe_pfn.py:25): classifier bounds drive
+    prereject_with_bounds in the support proposal."""
+    from npe_pfn_b200 import BoxUniform, run_tsnpe_pfn
+    torch.manual_seed(1)
+    prior = BoxUniform(-2 * torch.ones(2), 2 * torch.ones(2))
+    post = run_tsnpe_pfn(lambda t: t + 0.1 * torch.randn_like(t), prior, torch.zeros(1, 2), num_simulations=90,
+                         num_rounds=2, proposal_batch_size=100, simulation_batch_size=45,
+                         num_samples_to_estimate_support=100, allowed_false_negatives=0.05,
+                         regressor_init_kwargs={"engine": engine})
+    assert post._theta_train.shape == (90, 2) and bool(prior.support.check(post._theta_train).all())
+
+
 def test_tsnpe_rounds_autoregressive(engine):
     from npe_pfn_b200 import BoxUniform, run_tsnpe_pfn
     torch.manual_seed(0)
