@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--attn", default=None, choices=[None, "mma", "tc"])
     ap.add_argument("--gemm", default=None, choices=[None, "mma", "tc"])
     ap.add_argument("--attn-poly", type=int, default=None)
+    ap.add_argument("--opt", action="append", default=[], help="engine option key=value (tuning sweeps)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -219,6 +220,9 @@ def main():
         eng.set_option("gemm_impl", 1 if args.gemm == "tc" else 0)
     if args.attn_poly is not None:
         eng.set_option("attn_poly", args.attn_poly)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        eng.set_option(k, int(v))
     post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"engine": eng})
     post.rank_row_offset = rank << 40
     post.append_simulations(theta_p, x_p)

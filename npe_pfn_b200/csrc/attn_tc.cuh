@@ -38,6 +38,9 @@ struct TcArgs {
     int64_t R, N;
     int kv_ctx_mode;  // 0: K/V map dims (64, N, T) box (32,64,1); 1: dims (ld, T, N) box (32,1,64)
     int kx0, kx_head, v_dx;  // x coordinate of K for head 0, per-head step, V = K + v_dx
+    int heads, n_qtiles;     // work item = (column t, query tile, head): item = (t * n_qtiles + qt) * heads + h
+    int64_t items;
+    uint32_t wait_ticks;     // suspend-time hint of the producer / MMA threads' barrier waits (0 = none)
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -58,6 +61,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         "@p bra WAIT_DONE;\n\t"
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+// same, with a suspend-time hint (ns) so the hardware parks the thread longer before reporting "not yet"
+__device__ __forceinline__ void mbar_wait_hint(uint32_t bar, uint32_t parity, uint32_t ticks) {
+    if (ticks == 0) { mbar_wait(bar, parity); return; }
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAITH_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAITH_DONE;\n\t"
+        "bra WAITH_LOOP;\n\t"
+        "WAITH_DONE:\n\t}" ::"r"(bar), "r"(parity), "r"(ticks) : "memory");
 }
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
     asm volatile(
@@ -154,13 +168,13 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t bar_p = bar_q + 24;                     // [2] P_j written into S buffer b       softmax -> MMA
     const uint32_t bar_pv = bar_q + 40;                    // O += P_j V_j finished (rescale guard) MMA -> softmax
     const uint32_t bar_o = bar_q + 48;                     // last O += P V finished
-    const uint32_t tmem_slot = bar_q + 56;                 // [2]: S/P columns, O columns
+    const uint32_t bar_q_empty = bar_q + 56;               // the item's S MMAs have finished reading Q
+    const uint32_t tmem_slot = bar_q + 64;                 // [2]: S/P columns, O columns
     uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(tc_smem_raw + (tmem_slot - raw));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int h = blockIdx.y, t = blockIdx.z;
-    const int64_t m0 = (int64_t)blockIdx.x * TC_BM;
     const int ntiles = (int)((p.N + TC_BN - 1) / TC_BN);
+    const int per_col = p.n_qtiles * p.heads;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) {
@@ -168,6 +182,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             mbar_init(bar_kv_empty + 8 * s, 1);
         }
         mbar_init(bar_q, 1);
+        mbar_init(bar_q_empty, 1);
         mbar_init(bar_s, 1);
         mbar_init(bar_s + 8, 1);
         mbar_init(bar_p, 128);
@@ -189,174 +204,192 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tmem = tmem_slot_ptr[0];     // S/P double buffer
     const uint32_t tmem_o = tmem_slot_ptr[1];   // O accumulator
 
+    // Persistent: every role walks the same sequence of work items; barrier phases are carried across items through
+    // running counters (g = key tiles processed so far, qn = items processed so far).
     if (warp == 4) {
         // ================= TMA producer =================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmQ)) : "memory");
             asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(&tmKV)) : "memory");
-            mbar_expect_tx(bar_q, TC_Q_BYTES);
-            tma_load_3d(sQ, &tmQ, bar_q, h * kDh, t, (int)m0);
-            const int kx = p.kx0 + h * p.kx_head;
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % TC_STAGES;
-                const uint32_t ph = (uint32_t)(j / TC_STAGES) & 1u;
-                mbar_wait(bar_kv_empty + 8 * s, ph ^ 1u);
-                mbar_expect_tx(bar_kv_full + 8 * s, TC_STAGE_BYTES);
-                const uint32_t dstK = sKV + s * TC_STAGE_BYTES, dstV = dstK + TC_TILE_BYTES;
-                const int key0 = j * TC_BN;
-                if (p.kv_ctx_mode) {
-                    tma_load_3d(dstK, &tmKV, bar_kv_full + 8 * s, kx, t, key0);
-                    tma_load_3d(dstV, &tmKV, bar_kv_full + 8 * s, kx + p.v_dx, t, key0);
-                } else {
-                    tma_load_3d(dstK, &tmKV, bar_kv_full + 8 * s, kx, key0, t);
-                    tma_load_3d(dstV, &tmKV, bar_kv_full + 8 * s, kx + p.v_dx, key0, t);
+            uint32_t g = 0, qn = 0;
+            for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x, ++qn) {
+                const int t = (int)(item / per_col), rem = (int)(item % per_col);
+                const int qt = rem / p.heads, h = rem % p.heads;
+                mbar_wait_hint(bar_q_empty, (qn & 1u) ^ 1u, p.wait_ticks);  // the previous item's S = Q K^T MMAs have finished reading Q
+                mbar_expect_tx(bar_q, TC_Q_BYTES);
+                tma_load_3d(sQ, &tmQ, bar_q, h * kDh, t, qt * TC_BM);
+                const int kx = p.kx0 + h * p.kx_head;
+                for (int j = 0; j < ntiles; ++j, ++g) {
+                    const uint32_t s = g % TC_STAGES, ph = (g / TC_STAGES) & 1u;
+                    mbar_wait_hint(bar_kv_empty + 8 * s, ph ^ 1u, p.wait_ticks);
+                    mbar_expect_tx(bar_kv_full + 8 * s, TC_STAGE_BYTES);
+                    const uint32_t dstK = sKV + s * TC_STAGE_BYTES, dstV = dstK + TC_TILE_BYTES;
+                    const int key0 = j * TC_BN;
+                    if (p.kv_ctx_mode) {
+                        tma_load_3d(dstK, &tmKV, bar_kv_full + 8 * s, kx, t, key0);
+                        tma_load_3d(dstV, &tmKV, bar_kv_full + 8 * s, kx + p.v_dx, t, key0);
+                    } else {
+                        tma_load_3d(dstK, &tmKV, bar_kv_full + 8 * s, kx, key0, t);
+                        tma_load_3d(dstV, &tmKV, bar_kv_full + 8 * s, kx + p.v_dx, key0, t);
+                    }
                 }
             }
         }
     } else if (warp == 5) {
         // ================= MMA issuer (one thread) =================
-        // Issue order: QK_0, QK_1, then per tile j: [wait P_j] PV_j, QK_{j+2}.  tcgen05.mma executes in issue
-        // order, so QK_{j+2} (which overwrites S buffer j%2 = P_j) cannot pass PV_j, and the softmax warps always
-        // find S_{j+1} ready when they finish tile j.
+        // Issue order inside an item: QK_0, QK_1, then per tile j: [wait P_j] PV_j, QK_{j+2}.  tcgen05.mma executes in
+        // issue order, so QK_{j+2} (which overwrites S buffer = P_j) cannot pass PV_j, and the softmax warps always
+        // find S_{j+1} ready when they finish tile j.  The next item's first PV overwrites O only after its own P_0
+        // barrier, which every softmax thread reaches after it has read the previous item's O.
         if (lane == 0) {
             constexpr uint32_t idesc_qk = umma_idesc_bf16(TC_BM, TC_BN, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, kDh, 0, 1);
             const uint64_t descQ = umma_desc_sw64(sQ);
-            auto issue_qk = [&](int j) {
-                const int s = j % TC_STAGES;
-                mbar_wait(bar_kv_full + 8 * s, (uint32_t)(j / TC_STAGES) & 1u);
-                tc_fence_after();
-                const uint64_t descK = umma_desc_sw64(sKV + s * TC_STAGE_BYTES);
-                const uint32_t d = tmem + (uint32_t)((j & 1) * TC_BN);
+            uint32_t g0 = 0, qn = 0;  // g0 = global index of this item's first key tile
+            for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x, ++qn, g0 += (uint32_t)ntiles) {
+                auto issue_qk = [&](int j) {
+                    const uint32_t g = g0 + (uint32_t)j, s = g % TC_STAGES;
+                    mbar_wait_hint(bar_kv_full + 8 * s, (g / TC_STAGES) & 1u, p.wait_ticks);
+                    tc_fence_after();
+                    const uint64_t descK = umma_desc_sw64(sKV + s * TC_STAGE_BYTES);
+                    const uint32_t d = tmem + (g & 1u) * TC_BN;
 #pragma unroll
-                for (int kk = 0; kk < 2; ++kk)  // dh = 32 = 2 x K16; 32 bytes per step inside the swizzle atom
-                    umma_ss(d, descQ + (uint64_t)(kk * 2), descK + (uint64_t)(kk * 2), idesc_qk, kk > 0);
-                tc_commit(bar_s + 8 * (j & 1));
-            };
-            mbar_wait(bar_q, 0);
-            issue_qk(0);
-            if (ntiles > 1) issue_qk(1);
-            for (int j = 0; j < ntiles; ++j) {
-                const int s = j % TC_STAGES, b = j & 1;
-                mbar_wait(bar_p + 8 * b, (uint32_t)(j >> 1) & 1u);
-                tc_fence_after();
-                const uint64_t descV = umma_desc_sw64(sKV + s * TC_STAGE_BYTES + TC_TILE_BYTES);
-                const uint32_t pa = tmem + (uint32_t)(b * TC_BN);
+                    for (int kk = 0; kk < 2; ++kk)  // dh = 32 = 2 x K16; 32 bytes per step inside the swizzle atom
+                        umma_ss(d, descQ + (uint64_t)(kk * 2), descK + (uint64_t)(kk * 2), idesc_qk, kk > 0);
+                    tc_commit(bar_s + 8 * (g & 1u));
+                    if (j == ntiles - 1) tc_commit(bar_q_empty);
+                };
+                mbar_wait_hint(bar_q, qn & 1u, p.wait_ticks);
+                issue_qk(0);
+                if (ntiles > 1) issue_qk(1);
+                for (int j = 0; j < ntiles; ++j) {
+                    const uint32_t g = g0 + (uint32_t)j, s = g % TC_STAGES, b = g & 1u;
+                    mbar_wait_hint(bar_p + 8 * b, (g >> 1) & 1u, p.wait_ticks);
+                    tc_fence_after();
+                    const uint64_t descV = umma_desc_sw64(sKV + s * TC_STAGE_BYTES + TC_TILE_BYTES);
+                    const uint32_t pa = tmem + b * TC_BN;
 #pragma unroll
-                for (int kk = 0; kk < TC_BN / 16; ++kk)  // 16 keys per step: 8 TMEM columns of P, 1 KB of V
-                    umma_ts(tmem_o, pa + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
-                tc_commit(bar_kv_empty + 8 * s);
-                tc_commit(bar_pv);
-                if (j + 2 < ntiles) issue_qk(j + 2);
+                    for (int kk = 0; kk < TC_BN / 16; ++kk)  // 16 keys per step: 8 TMEM columns of P, 1 KB of V
+                        umma_ts(tmem_o, pa + kk * 8, descV + (uint64_t)(kk * 64), idesc_pv, (j > 0) || (kk > 0));
+                    tc_commit(bar_kv_empty + 8 * s);
+                    tc_commit(bar_pv);
+                    if (j + 2 < ntiles) issue_qk(j + 2);
+                }
+                tc_commit(bar_o);
             }
-            tc_commit(bar_o);
         }
     } else {
         // ================= softmax warps: thread = query row = TMEM lane =================
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         const uint32_t orow = tmem_o + ((uint32_t)(warp * 32) << 16);
         const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
-        float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f;
-        for (int j = 0; j < ntiles; ++j) {
-            const int b = j & 1;
-            const uint32_t scol = trow + (uint32_t)(b * TC_BN);
-            mbar_wait(bar_s + 8 * b, (uint32_t)(j >> 1) & 1u);
-            tc_fence_after();
-            // pass 1: both 32-column halves -> tile maximum (the second half is re-read later instead of being
-            // kept live, so the kernel fits the 112 registers that three CTAs per SM allow)
-            uint32_t sa[32], sb[32];
-            tmem_ld32(scol, sa);
-            tmem_ld32(scol + 32, sb);
-            tmem_wait_ld();
-            const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
-            if (nvalid < TC_BN) {
+        uint32_t g = 0, qn = 0;
+        for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x, ++qn) {
+            const int t = (int)(item / per_col), rem = (int)(item % per_col);
+            const int qt = rem / p.heads, h = rem % p.heads;
+            const int64_t m0 = (int64_t)qt * TC_BM;
+            float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f;
+            for (int j = 0; j < ntiles; ++j, ++g) {
+                const uint32_t b = g & 1u;
+                const uint32_t scol = trow + b * TC_BN;
+                mbar_wait(bar_s + 8 * b, (g >> 1) & 1u);
+                tc_fence_after();
+                // pass 1: both 32-column halves -> tile maximum (the second half is re-read later instead of being
+                // kept live, so the kernel fits the 112 registers that three CTAs per SM allow)
+                uint32_t sa[32], sb[32];
+                tmem_ld32(scol, sa);
+                tmem_ld32(scol + 32, sb);
+                tmem_wait_ld();
+                const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
+                if (nvalid < TC_BN) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        if (i >= nvalid) sa[i] = 0xff800000u;  // -inf
+                        if (32 + i >= nvalid) sb[i] = 0xff800000u;
+                    }
+                }
+                float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    if (i >= nvalid) sa[i] = 0xff800000u;  // -inf
-                    if (32 + i >= nvalid) sb[i] = 0xff800000u;
+                    mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
+                    mx1 = fmaxf(mx1, __uint_as_float(sb[i]));
                 }
-            }
-            float mx0 = -INFINITY, mx1 = -INFINITY;
+                const float mt = fmaxf(mx0, mx1) * sc;
+                if (j == 0) {
+                    m_ref = mt;
+                } else {
+                    // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
+                    const bool need = mt > m_ref + 8.0f;
+                    if (__any_sync(0xffffffffu, need)) {
+                        const float corr = need ? fast_exp2(m_ref - mt) : 1.0f;
+                        if (need) m_ref = mt;
+                        l0 *= corr;
+                        l1 *= corr;
+                        mbar_wait(bar_pv, (g - 1u) & 1u);  // O += P_{j-1} V_{j-1} must have landed
+                        tc_fence_after();
+                        uint32_t ov[32];
+                        tmem_ld32(orow, ov);
+                        tmem_wait_ld();
 #pragma unroll
-            for (int i = 0; i < 32; ++i) {
-                mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
-                mx1 = fmaxf(mx1, __uint_as_float(sb[i]));
-            }
-            const float mt = fmaxf(mx0, mx1) * sc;
-            if (j == 0) {
-                m_ref = mt;
-            } else {
-                // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
-                const bool need = mt > m_ref + 8.0f;
-                if (__any_sync(0xffffffffu, need)) {
-                    const float corr = need ? fast_exp2(m_ref - mt) : 1.0f;
-                    if (need) m_ref = mt;
-                    l0 *= corr;
-                    l1 *= corr;
-                    mbar_wait(bar_pv, (uint32_t)(j - 1) & 1u);  // O += P_{j-1} V_{j-1} must have landed
-                    tc_fence_after();
-                    uint32_t ov[32];
-                    tmem_ld32(orow, ov);
-                    tmem_wait_ld();
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                    tmem_st32(orow, ov);
+                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                        tmem_st32(orow, ov);
+                    }
                 }
-            }
-            // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs; first half from registers, second half re-read
-            uint32_t pk[32];
+                // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs; first half from registers, second half re-read
+                uint32_t pk[32];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
-                const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
-                const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
-                const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
-                const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
-                l0 += p0;
-                l1 += p1;
-                pk[i] = pack_bf16x2(p0, p1);
+                for (int i = 0; i < 16; ++i) {
+                    const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
+                    const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
+                    const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
+                    const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
+                    const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
+                    l0 += p0;
+                    l1 += p1;
+                    pk[i] = pack_bf16x2(p0, p1);
+                }
+                tmem_ld32(scol + 32, sa);
+                tmem_wait_ld();
+                if (nvalid < TC_BN) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (32 + i >= nvalid) sa[i] = 0xff800000u;
+                }
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
+                    const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
+                    const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
+                    const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
+                    const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
+                    l0 += p0;
+                    l1 += p1;
+                    pk[16 + i] = pack_bf16x2(p0, p1);
+                }
+                tmem_st32(scol, pk);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(bar_p + 8 * b);
             }
-            tmem_ld32(scol + 32, sa);
+            // ---- epilogue: O / l -> bf16 -> global ----
+            mbar_wait(bar_o, qn & 1u);
+            tc_fence_after();
+            uint32_t ov[32];
+            tmem_ld32(orow, ov);
             tmem_wait_ld();
-            if (nvalid < TC_BN) {
+            const int64_t r = m0 + warp * 32 + lane;
+            if (r < p.R) {
+                const float inv = 1.0f / (l0 + l1);
+                uint4* dst = reinterpret_cast<uint4*>(p.O + r * p.o_row + (int64_t)t * p.o_tok + h * kDh);
 #pragma unroll
-                for (int i = 0; i < 32; ++i)
-                    if (32 + i >= nvalid) sa[i] = 0xff800000u;
-            }
-#pragma unroll
-            for (int i = 0; i < 16; ++i) {
-                const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
-                const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
-                const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
-                const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
-                const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
-                l0 += p0;
-                l1 += p1;
-                pk[16 + i] = pack_bf16x2(p0, p1);
-            }
-            tmem_st32(scol, pk);
-            tmem_wait_st();
-            tc_fence_before();
-            mbar_arrive(bar_p + 8 * b);
-        }
-        // ---- epilogue: O / l -> bf16 -> global ----
-        mbar_wait(bar_o, 0);
-        tc_fence_after();
-        uint32_t ov[32];
-        tmem_ld32(orow, ov);
-        tmem_wait_ld();
-        const int64_t r = m0 + warp * 32 + lane;
-        if (r < p.R) {
-            const float inv = 1.0f / (l0 + l1);
-            uint4* dst = reinterpret_cast<uint4*>(p.O + r * p.o_row + (int64_t)t * p.o_tok + h * kDh);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                uint4 v;
-                v.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
-                v.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
-                v.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
-                v.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
-                dst[q] = v;
+                for (int q = 0; q < 4; ++q) {
+                    uint4 v;
+                    v.x = pack_bf16x2(__uint_as_float(ov[8 * q + 0]) * inv, __uint_as_float(ov[8 * q + 1]) * inv);
+                    v.y = pack_bf16x2(__uint_as_float(ov[8 * q + 2]) * inv, __uint_as_float(ov[8 * q + 3]) * inv);
+                    v.z = pack_bf16x2(__uint_as_float(ov[8 * q + 4]) * inv, __uint_as_float(ov[8 * q + 5]) * inv);
+                    v.w = pack_bf16x2(__uint_as_float(ov[8 * q + 6]) * inv, __uint_as_float(ov[8 * q + 7]) * inv);
+                    dst[q] = v;
+                }
             }
         }
     }
@@ -415,7 +448,8 @@ static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUten
     return cudaGetLastError();
 }
 
-static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, int poly_mod, cudaStream_t st) {
+static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, int poly_mod, int num_sms, int persist,
+                                         uint32_t wait_ticks, cudaStream_t st) {
     CUtensorMap mq, mkv;
     TcArgs p{};
     p.O = a.O; p.o_row = a.o_row; p.o_tok = a.o_tok; p.R = a.R; p.N = a.N;
@@ -437,7 +471,12 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, in
             return cudaErrorInvalidValue;
         p.kv_ctx_mode = 0; p.kx0 = 0; p.kx_head = 0; p.v_dx = a.v_off;
     }
-    dim3 grid((unsigned)ceil_div(a.R, TC_BM), (unsigned)heads, (unsigned)T);
+    p.heads = heads;
+    p.n_qtiles = (int)ceil_div(a.R, TC_BM);
+    p.items = (int64_t)T * p.n_qtiles * heads;
+    p.wait_ticks = wait_ticks;
+    // persist: 3 CTAs per SM walk the items; otherwise one CTA per item (the hardware scheduler staggers them)
+    dim3 grid((unsigned)(persist ? std::min<int64_t>(p.items, 3 * (int64_t)num_sms) : p.items));
     switch (poly_mod) {
         case 0: return launch_attn_tc_impl<0>(mq, mkv, p, grid, st);
         case 2: return launch_attn_tc_impl<2>(mq, mkv, p, grid, st);
