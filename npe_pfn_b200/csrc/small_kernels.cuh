@@ -453,9 +453,20 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(HeadArgs a) {
         }
         m = warp_max(m);
         __syncwarp();
-        unsigned long long z = 0ull;
-        for (int i = lane; i < B; i += 32) z += quantize_q40(exp_det(row[i] - m));
-        const unsigned long long Z = warp_sum_u64(z);
+        // bucket masses are integers, so partial sums are order-independent: every lane sums a CONTIGUOUS segment
+        // of buckets (no shuffles in the pass over the row); the inclusive scan of the 32 segment sums gives the
+        // partition sum and, when sampling, the segment that holds the target.
+        const int seg = (B + 31) >> 5;
+        const int s0 = min(lane * seg, B), s1 = min(s0 + seg, B);
+        unsigned long long ssum = 0ull;
+        for (int i = s0; i < s1; ++i) ssum += quantize_q40(exp_det(row[i] - m));
+        unsigned long long sinc = ssum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, sinc, o);
+            if (lane >= o) sinc += t;
+        }
+        const unsigned long long Z = __shfl_sync(0xffffffffu, sinc, 31);
         const double logZ = log((double)Z) - kLn2x40;
 
         if (!SAMPLE) {
@@ -480,30 +491,36 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(HeadArgs a) {
             u = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;  // strictly inside (0, 1)
         }
         const double target = (double)u * (double)Z;
-        unsigned long long run = 0ull;  // sum of all buckets before this chunk
+        // first segment whose inclusive sum is not below the target (sums are non-decreasing)
+        const unsigned sbal = __ballot_sync(0xffffffffu, (double)sinc < target);
+        const int sseg = __popc(sbal);
         int idx = -1;
         unsigned long long Cprev = 0ull, qsel = 0ull;
-        for (int base = 0; base < B && idx < 0; base += 32) {
-            const int i = base + lane;
-            const unsigned long long q = i < B ? quantize_q40(exp_det(row[i] - m)) : 0ull;
-            unsigned long long c = q;  // inclusive scan over lanes
+        if (sseg < 32) {
+            const unsigned long long segprev = __shfl_sync(0xffffffffu, sinc - ssum, sseg);  // mass before the segment
+            const int b0 = min(sseg * seg, B), b1 = min(b0 + seg, B);
+            unsigned long long run = segprev;
+            for (int base = b0; base < b1 && idx < 0; base += 32) {
+                const int i = base + lane;
+                const unsigned long long q = i < b1 ? quantize_q40(exp_det(row[i] - m)) : 0ull;
+                unsigned long long c = q;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long t = __shfl_up_sync(0xffffffffu, c, o);
-                if (lane >= o) c += t;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long t = __shfl_up_sync(0xffffffffu, c, o);
+                    if (lane >= o) c += t;
+                }
+                c += run;
+                const bool below = (i < b1) && ((double)c < target);
+                const int nbelow = __popc(__ballot_sync(0xffffffffu, below));
+                const int nvalid = min(32, b1 - base);
+                if (nbelow < nvalid) {
+                    idx = base + nbelow;
+                    const unsigned long long csel = __shfl_sync(0xffffffffu, c, nbelow);
+                    qsel = __shfl_sync(0xffffffffu, q, nbelow);
+                    Cprev = csel - qsel;
+                }
+                run = __shfl_sync(0xffffffffu, c, 31);
             }
-            c += run;
-            const bool below = (i < B) && ((double)c < target);
-            const unsigned bal = __ballot_sync(0xffffffffu, below);
-            const int nbelow = __popc(bal);
-            const int nvalid = min(32, B - base);
-            if (nbelow < nvalid) {  // the first lane that is not below holds the bucket
-                idx = base + nbelow;
-                const unsigned long long csel = __shfl_sync(0xffffffffu, c, nbelow);
-                qsel = __shfl_sync(0xffffffffu, q, nbelow);
-                Cprev = csel - qsel;
-            }
-            run = __shfl_sync(0xffffffffu, c, 31);
         }
         if (idx < 0) { idx = B - 1; Cprev = Z; qsel = 0ull; }
         if (lane == 0) {
