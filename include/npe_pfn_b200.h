@@ -114,6 +114,12 @@ int pfn_accept_compact(pfn_ctx* ctx, const float* theta, int64_t ld, int64_t M, 
                        const float* hi, const uint8_t* mask, int64_t* out_idx, float* out_rows,
                        int64_t* out_count, void* stream);
 
+/* Context filter (support_posterior.py:357-369, called from get_context, npe_pfn.py:739-744): z-score the columns
+ * of x_train[Ntot, dx] (row stride ld), L2 distance of every row to obs[dx], indices of the k nearest rows in
+ * ascending distance (ties by index) -> out_idx[k]; out_dist[k] optional.  k <= 16384.  No host sync. */
+int pfn_filter_context(pfn_ctx* ctx, const float* x_train, int64_t ld, int64_t Ntot, int dx, const float* obs,
+                       int64_t k, int64_t* out_idx, float* out_dist, void* stream);
+
 /* introspection (host values) */
 int pfn_slot_info(pfn_ctx* ctx, int slot, int64_t* N, int32_t* F, int32_t* T, int64_t* kv_bytes);
 /* number of kernels this library launched since creation (bench.py's gpu_launches) */

@@ -24,6 +24,7 @@
 #include "gemm_tc.cuh"
 #endif
 #include "small_kernels.cuh"
+#include "filter_kernels.cuh"
 
 namespace pfn {
 std::string& last_error() {
@@ -77,6 +78,9 @@ struct pfn_ctx {
     int32_t* cp_counts = nullptr;
     int64_t* cp_offsets = nullptr;
     int64_t cp_cap = 0;
+    // context-filter scratch
+    uint8_t* flt_ws = nullptr;
+    int64_t flt_cap = 0;
     int64_t launches = 0;
     int64_t last_rows = 0;
     int last_T = 0;
@@ -428,6 +432,7 @@ int pfn_ctx_destroy(pfn_ctx* c) {
     cudaFree(c->logits);
     cudaFree(c->cp_counts);
     cudaFree(c->cp_offsets);
+    cudaFree(c->flt_ws);
     delete c;
     return 0;
 }
@@ -619,6 +624,69 @@ int pfn_accept_compact(pfn_ctx* c, const float* theta, int64_t ld, int64_t M, in
                                                                        out_idx, out_rows);
         PFN_LAUNCH_OK(c);
     }
+    return 0;
+}
+
+int pfn_filter_context(pfn_ctx* c, const float* x_train, int64_t ld, int64_t Ntot, int dx, const float* obs, int64_t k,
+                       int64_t* out_idx, float* out_dist, void* stream) {
+    PFN_REQUIRE(c && x_train && obs && out_idx, "null argument");
+    PFN_REQUIRE(Ntot >= 1 && dx >= 1 && ld >= dx, "bad shape");
+    PFN_REQUIRE(k >= 1 && k <= Ntot, "k must be in [1, Ntot]");
+    PFN_REQUIRE(k <= FLT_MAX_K, "k above 16384 is not supported by the single-CTA sort");
+    PFN_REQUIRE(Ntot < (1ll << 32), "at most 2^32 - 1 simulations");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    if (Ntot > c->flt_cap) {
+        PFN_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(c->flt_ws);
+        c->flt_ws = nullptr; c->flt_cap = 0;
+        // dist f32 | mask_lt u8 | mask_eq u8 | idx_lt i64 | idx_eq i64 | stats | hist | state | counts
+        const size_t bytes = (size_t)Ntot * (4 + 1 + 1 + 8 + 8) + 64 * 1024;
+        PFN_CUDA_OK(cudaMalloc(&c->flt_ws, bytes));
+        c->flt_cap = Ntot;
+    }
+    uint8_t* p = c->flt_ws;
+    int64_t* idx_lt = reinterpret_cast<int64_t*>(p); p += (size_t)c->flt_cap * 8;
+    int64_t* idx_eq = reinterpret_cast<int64_t*>(p); p += (size_t)c->flt_cap * 8;
+    float* dist = reinterpret_cast<float*>(p); p += (size_t)c->flt_cap * 4;
+    uint8_t* mask_lt = p; p += (size_t)c->flt_cap;
+    uint8_t* mask_eq = p; p += (size_t)c->flt_cap;
+    p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 255) & ~(uintptr_t)255);
+    float* stats = reinterpret_cast<float*>(p); p += 4096;
+    unsigned int* hist = reinterpret_cast<unsigned int*>(p); p += 1024;
+    unsigned long long* state = reinterpret_cast<unsigned long long*>(p); p += 64;
+    int64_t* counts = reinterpret_cast<int64_t*>(p);
+    PFN_REQUIRE(dx * 2 * 4 <= 4096, "too many x columns");
+
+    filter_stats_kernel<<<dx, 256, 0, st>>>(x_train, ld, Ntot, dx, stats);
+    PFN_LAUNCH_OK(c);
+    filter_dist_kernel<<<(unsigned)ceil_div(Ntot, 256), 256, 0, st>>>(x_train, ld, Ntot, dx, obs, stats, dist);
+    PFN_LAUNCH_OK(c);
+    const unsigned long long init[3] = {0ull, (unsigned long long)(k - 1), 0ull};
+    PFN_CUDA_OK(cudaMemcpyAsync(state, init, sizeof(init), cudaMemcpyHostToDevice, st));
+    PFN_CUDA_OK(cudaMemsetAsync(hist, 0, 1024, st));
+    const unsigned hb = (unsigned)std::min<int64_t>(ceil_div(Ntot, 256), 148 * 8);
+    for (int shift = 24; shift >= 0; shift -= 8) {
+        filter_hist_kernel<<<hb, 256, 0, st>>>(dist, Ntot, shift, state, hist);
+        PFN_LAUNCH_OK(c);
+        filter_pick_kernel<<<1, 32, 0, st>>>(hist, shift, state);
+        PFN_LAUNCH_OK(c);
+    }
+    filter_mask_kernel<<<(unsigned)ceil_div(Ntot, 256), 256, 0, st>>>(dist, Ntot, state, mask_lt, mask_eq);
+    PFN_LAUNCH_OK(c);
+    // ordered compaction of the two masks (row "theta" is unused: dim 1 view of dist keeps the finite check cheap)
+    if (int rc = pfn_accept_compact(c, dist, 1, Ntot, 1, nullptr, nullptr, mask_lt, idx_lt, nullptr, counts, stream)) return rc;
+    if (int rc = pfn_accept_compact(c, dist, 1, Ntot, 1, nullptr, nullptr, mask_eq, idx_eq, nullptr, counts + 1, stream)) return rc;
+    int npow2 = 1;
+    while (npow2 < k) npow2 <<= 1;
+    const size_t smem = (size_t)npow2 * 8;
+    static size_t smem_set = 0;
+    if (smem > 48 * 1024 && smem > smem_set) {
+        PFN_CUDA_OK(cudaFuncSetAttribute(filter_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        smem_set = smem;
+    }
+    filter_sort_kernel<<<1, 1024, smem, st>>>(dist, idx_lt, counts, idx_eq, k, npow2, out_idx, out_dist);
+    PFN_LAUNCH_OK(c);
     return 0;
 }
 

@@ -30,6 +30,7 @@ class pfn_model_config(ctypes.Structure):
 ABI_SYMBOLS = [
     "pfn_abi_version", "pfn_last_error", "pfn_ctx_create", "pfn_ctx_destroy", "pfn_set_option", "pfn_prefill",
     "pfn_forward_logits", "pfn_head_sample", "pfn_head_nll", "pfn_sample", "pfn_logprob", "pfn_accept_compact",
+    "pfn_filter_context",
     "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_debug_last_states",
 ]
 
@@ -74,6 +75,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_logprob.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp, f32, c.c_int, vp]
     L.pfn_accept_compact.restype = c.c_int
     L.pfn_accept_compact.argtypes = [vp, vp, i64, i64, c.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.pfn_filter_context.restype = c.c_int
+    L.pfn_filter_context.argtypes = [vp, vp, i64, i64, c.c_int, vp, i64, vp, vp, vp]
     L.pfn_slot_info.restype = c.c_int
     L.pfn_slot_info.argtypes = [vp, c.c_int, c.POINTER(i64), c.POINTER(i32), c.POINTER(i32), c.POINTER(i64)]
     L.pfn_launch_count.restype = i64
@@ -254,6 +257,17 @@ class Engine:
         self._check(self.lib.pfn_kernel_times(self._h, ms, cnt, fl, int(reset)))
         names = ["attn_test", "attn_ctx", "gemm", "other"]
         return {n: (ms[i], cnt[i], fl[i]) for i, n in enumerate(names)}
+
+    def filter_context(self, x_train: torch.Tensor, obs: torch.Tensor, k: int, want_dist: bool = False):
+        """Indices (int64, CUDA) of the k simulations nearest to `obs` in z-scored x, ascending distance."""
+        x_train = _f32_rows(x_train, self.device)
+        obs = obs.to(self.device, torch.float32).reshape(-1).contiguous()
+        N, dx = x_train.shape
+        idx = torch.empty(k, dtype=torch.int64, device=self.device)
+        dist = torch.empty(k, dtype=torch.float32, device=self.device) if want_dist else None
+        self._check(self.lib.pfn_filter_context(self._h, _ptr(x_train), x_train.stride(0) if N > 1 else dx, N, dx,
+                                                _ptr(obs), k, _ptr(idx), _ptr(dist), self._stream()))
+        return (idx, dist) if want_dist else idx
 
     def slot_info(self, slot: int):
         N, F, T, kv = c.c_int64(), c.c_int32(), c.c_int32(), c.c_int64()

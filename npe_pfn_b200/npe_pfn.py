@@ -77,6 +77,7 @@ class NPE_PFN_Core:
         state["_model"] = None
         state["_model_classifier"] = None
         state["_ctx"] = None
+        state.pop("_x_train_dev", None)
         return state
 
     def __setstate__(self, state):
@@ -517,9 +518,33 @@ class TabPFN_Based_NPE_PFN(NPE_PFN_Core):
         self.filter = get_filtering_method(filter_type)
         self.filter_context_size = filter_context_size
 
+    #: run `standardized_euclidean_filtering` on the GPU (`pfn_filter_context`) when it applies
+    device_filter = True
+
     def get_context(self, x: Tensor):
         x = self._validate_x(x)
+        if (self.device_filter and self.filter_type == "standardized_euclidean_filtering" and x.shape[0] == 1
+                and min(self.filter_context_size, self._x_train.shape[0]) <= 16384 and self._x_train.shape[0] > 1):
+            idx = self._device_filter_indices(x)
+            if idx is not None:
+                return self._theta_train[idx], self._x_train[idx]
         return self.filter(x, self._theta_train, self._x_train, self.filter_context_size)
+
+    def _device_filter_indices(self, x: Tensor):
+        """k nearest simulations in z-scored x, ordered by distance (support_posterior.py:357-369), on the device.
+        The device copy of the simulations is kept until `append_simulations` replaces them."""
+        eng = self.engine
+        cache = self.__dict__.get("_x_train_dev")
+        if cache is None or cache[0] != self._ctx_version:
+            xd = self._x_train.to(eng.device, torch.float32).contiguous()
+            if not bool((xd.std(dim=0) > 0).all()):  # the reference yields NaN distances here: keep its behaviour
+                self._x_train_dev = (self._ctx_version, None)
+                return None
+            self._x_train_dev = cache = (self._ctx_version, xd)
+        if cache[1] is None:
+            return None
+        k = min(self.filter_context_size, self._x_train.shape[0])
+        return eng.filter_context(cache[1], x[0], k).cpu()
 
     def _context_key(self, x: Tensor):
         if self.filter_type == "random_filtering" or callable(self.filter_type):

@@ -210,6 +210,43 @@ def test_slot_cache_not_shared_between_posteriors(engine):
             assert torch.equal(lp, ref[name])
 
 
+@pytest.mark.parametrize("Ntot,dx,k", [(50, 2, 50), (1000, 3, 100), (100_000, 10, 10_000), (1_000_000, 5, 10_000)])
+def test_context_filter_on_device(engine, Ntot, dx, k):
+    """pfn_filter_context against the reference's torch formula (support_posterior.py:357-369)."""
+    from npe_pfn_b200.support_posterior import standardized_euclidean_filtering
+    g = torch.Generator().manual_seed(Ntot)
+    x = torch.randn(Ntot, dx, generator=g) * torch.arange(1, dx + 1) + 0.5
+    theta = torch.arange(Ntot, dtype=torch.float32)[:, None]
+    obs = x[Ntot // 3:Ntot // 3 + 1] + 0.01
+    idx, dist = engine.filter_context(x, obs[0], k, want_dist=True)
+    idx, dist = idx.cpu(), dist.cpu()
+    th_ref, x_ref = standardized_euclidean_filtering(obs, theta, x, k)
+    idx_ref = th_ref[:, 0].long()
+    assert idx.shape == (k,) and len(set(idx.tolist())) == k
+    assert bool((dist[1:] >= dist[:-1]).all())  # ascending distance
+    mu, sd = x.mean(0), x.std(0)
+    d_all = torch.norm((x - mu) / sd - (obs - mu) / sd, dim=1)
+    assert torch.allclose(dist, d_all[idx], rtol=1e-4, atol=1e-5)
+    # same set up to near-ties at the cut-off, same order up to fp32 rounding of the distances
+    common = len(set(idx.tolist()) & set(idx_ref.tolist()))
+    assert common >= k - max(2, k // 1000)
+    assert float(d_all[idx].max()) <= float(d_all[idx_ref].max()) * (1 + 1e-4) + 1e-6
+    agree = (idx == idx_ref).float().mean().item()
+    assert agree >= 0.99 or k == Ntot
+
+
+def test_get_context_uses_device_filter(engine):
+    from npe_pfn_b200 import TabPFN_Based_NPE_PFN
+    theta, x, g = _toy(300, 3, 2, 12)
+    post = TabPFN_Based_NPE_PFN(filter_context_size=40, regressor_init_kwargs={"engine": engine})
+    post.append_simulations(theta, x)
+    th_d, x_d = post.get_context(x[5])
+    post.device_filter = False
+    th_h, x_h = post.get_context(x[5])
+    assert th_d.shape == (40, 2) and torch.equal(x_d[0], x[5])
+    assert torch.equal(th_d, th_h) and torch.equal(x_d, x_h)
+
+
 def test_accept_compact_matches_torch(engine):
     g = torch.Generator().manual_seed(3)
     for M, dim in [(1, 2), (255, 3), (256, 1), (100_003, 5)]:
