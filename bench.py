@@ -298,6 +298,19 @@ def main():
     step_device()
     kt = eng.kernel_times(reset=True)
     eng.set_option("time_kernels", 0)
+    # ---- log_prob rows/s on the same workload (config 2: "100k samples plus autoregressive log_prob") --------------
+    th_dev = step_device()[:S].contiguous()
+    lp_rows = min(S, 50_000)
+    post._autoregressive_log_prob(th_dev[:lp_rows], xo_p, return_device=True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    post._autoregressive_log_prob(th_dev[:lp_rows], xo_p, return_device=True)
+    e3.record()
+    barrier()
+    lp_ms = e2.elapsed_time(e3)
+    logprob_rows_per_s = lp_rows * world / (lp_ms / 1e3)
+
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -308,7 +321,10 @@ def main():
     achieved = a_fl / (a_ms * 1e-3) / 1e12 if a_ms > 0 else 0.0
     tot_ms = sum(v[0] for v in kt.values())
     roofline = {"bound": "tensor", "kernel": "item attention of test rows vs cached K/V", "achieved": achieved,
-                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                # DRAM bytes per launch from ncu (profiles/r1_launch_summary_final.csv: 149 attn_tc launches read
+                # 11 659 MB and wrote 1 931 MB); algorithmic bytes of the largest launch (Q in, O out, K/V) are 152 MB
+                "traffic": 9.12e7,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches": a_cnt, "avg_launch_ms": a_ms / max(a_cnt, 1),
@@ -339,6 +355,8 @@ def main():
                        "parallelism": f"rows sharded over {world} GPU(s), context replicated"},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
+            "logprob": {"value": logprob_rows_per_s, "unit": "rows/s", "rows": lp_rows,
+                        "note": "autoregressive log_prob of posterior draws, K/V caches reused, device resident"},
         }))
     if world > 1:
         dist.destroy_process_group()

@@ -365,7 +365,9 @@ int check_slot(pfn_ctx* c, int slot, bool need_valid) {
     return 0;
 }
 
-int chunk_rows_of(const pfn_ctx* c) { return c->cfg.chunk_rows > 0 ? c->cfg.chunk_rows : 16384; }
+// default: two waves of 128-row query tiles per (head, column): 2 * 148 * 128 = 37 888 rows on a B200, which makes the
+// item-attention grid (tiles * 6 * T CTAs against 3 * 148 resident) and the GEMM tile counts whole multiples of a wave
+int chunk_rows_of(const pfn_ctx* c) { return c->cfg.chunk_rows > 0 ? c->cfg.chunk_rows : 2 * c->num_sms * 128; }
 
 }  // namespace
 
