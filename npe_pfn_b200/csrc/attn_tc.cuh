@@ -437,7 +437,10 @@ static inline bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint
 template <int POLY_MOD>
 static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUtensorMap& mkv, const TcArgs& p, dim3 grid,
                                               cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<POLY_MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              TC_SMEM_BYTES);

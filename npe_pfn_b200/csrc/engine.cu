@@ -221,11 +221,8 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
     PFN_LAUNCH_OK(c);
 
     const size_t fa_smem = (size_t)FA_WARPS * 2 * T * 33 * sizeof(float);
-    static size_t fa_smem_set = 0;
-    if (fa_smem > 48 * 1024 && fa_smem > fa_smem_set) {
+    if (fa_smem > 48 * 1024)
         PFN_CUDA_OK(cudaFuncSetAttribute(feature_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fa_smem));
-        fa_smem_set = fa_smem;
-    }
 
     // The chain between two item-attention kernels runs sub-chunk by sub-chunk (one wave of 128-token tiles), so
     // its intermediates (feature-attention qkv, MLP hidden) live in small reused scratch buffers that stay in L2;
@@ -342,14 +339,9 @@ int decode_rows(pfn_ctx* c, const Slot& s, int64_t r0, int64_t n, float* out, in
 
 int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
     const size_t smem = (size_t)HEAD_WARPS * h.B * sizeof(float);
-    static size_t set_s = 0, set_n = 0;
-    if (sample && smem > set_s) {
-        PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_s = smem;
-    }
-    if (!sample && smem > set_n) {
-        PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        set_n = smem;
+    if (smem > 48 * 1024) {  // per device and cheap: set it every time
+        if (sample) PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(h.M, HEAD_WARPS), 148 * 8);
     if (sample) head_kernel<true><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
@@ -682,11 +674,8 @@ int pfn_filter_context(pfn_ctx* c, const float* x_train, int64_t ld, int64_t Nto
     int npow2 = 1;
     while (npow2 < k) npow2 <<= 1;
     const size_t smem = (size_t)npow2 * 8;
-    static size_t smem_set = 0;
-    if (smem > 48 * 1024 && smem > smem_set) {
+    if (smem > 48 * 1024)
         PFN_CUDA_OK(cudaFuncSetAttribute(filter_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        smem_set = smem;
-    }
     filter_sort_kernel<<<1, 1024, smem, st>>>(dist, idx_lt, counts, idx_eq, k, npow2, out_idx, out_dist);
     PFN_LAUNCH_OK(c);
     return 0;

@@ -183,7 +183,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_mma_kernel(GemmArgs p) {
 
 template <int EPI>
 static inline cudaError_t launch_gemm_mma(const GemmArgs& a, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_mma_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              GM_SMEM_BYTES);

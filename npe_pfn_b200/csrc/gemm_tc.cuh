@@ -380,7 +380,10 @@ static inline bool make_map2_out(CUtensorMap* m, const void* base, bool fp32, ui
 
 template <int EPI>
 static inline cudaError_t launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStream_t st) {
-    static bool configured = false;
+    static bool configured_dev[64] = {};  // the attribute is per device
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
     if (!configured) {
         cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES);
         if (e != cudaSuccess) return e;
