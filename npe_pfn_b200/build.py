@@ -28,11 +28,29 @@ def _sources():
     return out
 
 
+def _source_hash() -> str:
+    import hashlib
+    h = hashlib.sha256()
+    for path in sorted(os.path.realpath(p) for p in _sources()):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+HASH_PATH = LIB_PATH + ".srchash"
+
+
 def is_stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    """Content based (file times do not survive being copied to the GPU box): the library is current when the
+    hash of the sources it was built from equals the hash of the sources in the tree."""
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    t = os.path.getmtime(LIB_PATH)
-    return any(os.path.getmtime(s) > t for s in _sources())
+    try:
+        return open(HASH_PATH).read().strip() != _source_hash()
+    except OSError:
+        return True
 
 
 def build_library(force: bool = False, verbose: bool = False) -> str:
@@ -45,8 +63,12 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     flags = list(NVCC_FLAGS)
     if os.path.exists(os.path.join(CSRC, "attn_tc.cuh")):
         flags.append("-DPFN_WITH_ATTN_TC")
-    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH, os.path.join(CSRC, "engine.cu")]
+    tmp = LIB_PATH + ".tmp"
+    cmd = [nvcc] + flags + (["-Xptxas", "-v"] if verbose else []) + ["-o", tmp, os.path.join(CSRC, "engine.cu")]
     subprocess.check_call(cmd)
+    os.replace(tmp, LIB_PATH)
+    with open(HASH_PATH, "w") as f:
+        f.write(_source_hash())
     return LIB_PATH
 
 

@@ -65,7 +65,7 @@ def test_fit_statistics_and_borders(engine, weights, F, N):
     assert ex["N"] == N and ex["F"] == F and ex["T"] == (F + 1) // 2 + 1
 
 
-@pytest.mark.parametrize("F,N,M", [(1, 16, 8), (2, 64, 50), (3, 100, 33), (5, 200, 130), (10, 300, 64), (19, 150, 40),
+@pytest.mark.parametrize("F,N,M", [(2, 1, 3), (3, 2, 1), (1, 16, 8), (2, 64, 50), (3, 100, 33), (5, 200, 130), (10, 300, 64), (19, 150, 40),
                                    (40, 70, 20)])
 def test_logits_and_kv_cache_vs_oracle(engine, weights, F, N, M):
     from oracle.estimator import OracleTabPFNRegressor
