@@ -5,7 +5,8 @@ One "step" = one pass of the hot path on the `gaussian_linear` workload (BASELIN
 10-D x, N = 10 000 simulations as context, S posterior draws for one observation.  Every step rebuilds the
 per-dimension K/V caches (10 prefills) and then runs the 10 autoregressive dimensions, so nothing is carried over
 from a previous step.  With N GPUs every rank draws S samples (weak scaling, rows sharded, context replicated) and
-the finished draws are all-gathered over NCCL inside the timed region.
+the finished draws are all-gathered over NCCL inside the timed region; the per-dimension context prefills are split
+over the ranks and the finished K/V-cache slots broadcast over NCCL (every rank still ends up with all ten caches).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--samples S] [--impl ours|reference]
 
@@ -225,6 +226,7 @@ def main():
         eng.set_option(k, int(v))
     post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"engine": eng})
     post.rank_row_offset = rank << 40
+    post.shard_prefill = world > 1  # all ranks hold the same simulations and call sample() together
     post.append_simulations(theta_p, x_p)
 
     def barrier():
@@ -352,7 +354,9 @@ def main():
                        "weights": "seeded random init of the TabPFNv2 regressor architecture",
                        "prefill_in_step": True,
                        "l2": "per-step working set (1.3 GB of K/V cache + activations) exceeds the 126 MB L2",
-                       "parallelism": f"rows sharded over {world} GPU(s), context replicated"},
+                       "parallelism": f"rows sharded over {world} GPU(s), context replicated"
+                                      + ("; per-dimension prefills split over the ranks, slots broadcast over NCCL"
+                                         if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "logprob": {"value": logprob_rows_per_s, "unit": "rows/s", "rows": lp_rows,

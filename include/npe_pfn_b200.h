@@ -133,6 +133,13 @@ int pfn_kernel_times(pfn_ctx* ctx, double* ms, int64_t* counts, double* flops, i
  * kv[L][T][N][64] bf16 (K 0..31 | V 32..63). */
 int pfn_slot_export(pfn_ctx* ctx, int slot, float* stats, float* y_stats, float* borders, void* kv,
                     void* stream);
+/* Slot transfer (prefills of different dimensions are independent, so ranks can split them and exchange the results
+ * over NCCL): pfn_slot_state copies the raw encoder-statistics block (452 floats: mean[128] | std[128] | scale[64] |
+ * y_mean, y_std, y_fill, 0) to a device buffer; pfn_slot_import installs a slot from that block, its bucket borders
+ * [num_buckets + 1] and its K/V cache [L][T][N][64] bf16 (all device pointers), as pfn_slot_export produced them. */
+int pfn_slot_state(pfn_ctx* ctx, int slot, float* enc_state, void* stream);
+int pfn_slot_import(pfn_ctx* ctx, int slot, int64_t N, int F, const float* enc_state, const float* borders,
+                    const void* kv, void* stream);
 /* debug / parity: final-layer states of the last forward chunk [rows, T, E] fp32 */
 int pfn_debug_last_states(pfn_ctx* ctx, float* out, int64_t max_floats, void* stream);
 

@@ -731,6 +731,39 @@ int pfn_slot_export(pfn_ctx* c, int slot, float* stats, float* y_stats, float* b
     return 0;
 }
 
+int pfn_slot_import(pfn_ctx* c, int slot, int64_t N, int F, const float* enc_state, const float* borders, const void* kv,
+                    void* stream) {
+    if (int rc = check_slot(c, slot, false)) return rc;
+    PFN_REQUIRE(enc_state && borders && kv, "null data pointer");
+    PFN_REQUIRE(N >= 1 && F >= 1 && F <= 2 * c->cfg.max_groups, "bad shape");
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    Slot& s = c->slots[slot];
+    s.valid = false;
+    s.N = N; s.F = F; s.G = (F + 1) / 2; s.T = s.G + 1;
+    const size_t need = (size_t)c->cfg.nlayers * s.T * N * kKvRow * sizeof(bf16);
+    if (need > s.kv_cap) {
+        PFN_CUDA_OK(cudaStreamSynchronize(st));
+        if (s.kv) PFN_CUDA_OK(cudaFree(s.kv));
+        s.kv = nullptr; s.kv_cap = 0;
+        PFN_CUDA_OK(cudaMalloc(&s.kv, need));
+        s.kv_cap = need;
+    }
+    PFN_CUDA_OK(cudaMemcpyAsync(s.enc, enc_state, kEncFloats * 4, cudaMemcpyDeviceToDevice, st));
+    PFN_CUDA_OK(cudaMemcpyAsync(s.borders, borders, (size_t)(c->cfg.num_buckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+    PFN_CUDA_OK(cudaMemcpyAsync(s.kv, kv, need, cudaMemcpyDeviceToDevice, st));
+    s.valid = true;
+    return 0;
+}
+
+int pfn_slot_state(pfn_ctx* c, int slot, float* enc_state, void* stream) {
+    if (int rc = check_slot(c, slot, true)) return rc;
+    PFN_REQUIRE(enc_state, "null data pointer");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    PFN_CUDA_OK(cudaMemcpyAsync(enc_state, c->slots[slot].enc, kEncFloats * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
 int pfn_debug_last_states(pfn_ctx* c, float* out, int64_t max_floats, void* stream) {
     PFN_REQUIRE(c && out, "null argument");
     const int64_t n = c->last_rows * c->last_T * kE;

@@ -31,7 +31,8 @@ ABI_SYMBOLS = [
     "pfn_abi_version", "pfn_last_error", "pfn_ctx_create", "pfn_ctx_destroy", "pfn_set_option", "pfn_prefill",
     "pfn_forward_logits", "pfn_head_sample", "pfn_head_nll", "pfn_sample", "pfn_logprob", "pfn_accept_compact",
     "pfn_filter_context",
-    "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_debug_last_states",
+    "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_slot_state", "pfn_slot_import",
+    "pfn_debug_last_states",
 ]
 
 _LIB = None
@@ -85,6 +86,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_kernel_times.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i64), c.POINTER(c.c_double), c.c_int]
     L.pfn_slot_export.restype = c.c_int
     L.pfn_slot_export.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp]
+    L.pfn_slot_state.restype = c.c_int
+    L.pfn_slot_state.argtypes = [vp, c.c_int, vp, vp]
+    L.pfn_slot_import.restype = c.c_int
+    L.pfn_slot_import.argtypes = [vp, c.c_int, i64, c.c_int, vp, vp, vp, vp]
     L.pfn_debug_last_states.restype = c.c_int
     L.pfn_debug_last_states.argtypes = [vp, vp, i64, vp]
     _LIB = L
@@ -288,6 +293,22 @@ class Engine:
         Fp = 2 * G
         return {"mean": stats[:Fp], "std": stats[Fp:2 * Fp], "scale": stats[2 * Fp:2 * Fp + G], "y_mean": ystats[0],
                 "y_std": ystats[1], "y_fill": ystats[2], "borders": borders, "kv": kv, **info}
+
+    ENC_STATE_FLOATS = 2 * 128 + 64 + 4
+
+    def slot_pack(self, slot: int):
+        """Everything `prefill` produced for a slot, as device tensors (for a broadcast to other ranks)."""
+        info = self.slot_info(slot)
+        enc = torch.empty(self.ENC_STATE_FLOATS, dtype=torch.float32, device=self.device)
+        self._check(self.lib.pfn_slot_state(self._h, slot, _ptr(enc), self._stream()))
+        borders = torch.empty(self.cfg.num_buckets + 1, dtype=torch.float32, device=self.device)
+        kv = torch.empty(self.cfg.nlayers, info["T"], info["N"], 64, dtype=torch.bfloat16, device=self.device)
+        self._check(self.lib.pfn_slot_export(self._h, slot, None, None, _ptr(borders), _ptr(kv), self._stream()))
+        return enc, borders, kv
+
+    def slot_unpack(self, slot: int, N: int, F: int, enc: torch.Tensor, borders: torch.Tensor, kv: torch.Tensor):
+        assert enc.is_cuda and borders.is_cuda and kv.is_cuda and kv.is_contiguous()
+        self._check(self.lib.pfn_slot_import(self._h, slot, N, F, _ptr(enc), _ptr(borders), _ptr(kv), self._stream()))
 
     def last_states(self, rows: int, T: int) -> torch.Tensor:
         out = torch.empty(rows, T, self.cfg.emsize, dtype=torch.float32, device=self.device)

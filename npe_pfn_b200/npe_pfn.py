@@ -70,6 +70,9 @@ class NPE_PFN_Core:
         self._prior_bounds = "unset"
         #: extra Philox row offset (distinct per rank when draws are sharded over GPUs)
         self.rank_row_offset = 0
+        #: opt-in for multi-GPU jobs whose ranks hold the SAME simulations and call sample / log_prob together:
+        #: split the per-dimension prefills over the ranks and exchange the slots over NCCL (`prefill_sharded`)
+        self.shard_prefill = False
 
     # -- pickling: drop the engine-backed model, rebuild from kwargs (npe_pfn.py:57-71) --------------
     def __getstate__(self):
@@ -159,6 +162,41 @@ class NPE_PFN_Core:
             self._ensure_slot(ctx, d)
         return self
 
+    def prefill_sharded(self, x: Tensor):
+        """Like `prefill`, with the per-dimension prefills split over the ranks of the default process group: rank r
+        builds dimensions d = r, r + W, ... and every finished slot (statistics, borders, K/V cache) is broadcast
+        from its owner over NCCL.  The context must be identical on all ranks (it is replicated)."""
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+            return self.prefill(x)
+        rank, world = dist.get_rank(), dist.get_world_size()
+        x = self._validate_x(x)
+        ctx = self._prepare_context(x)
+        eng = self.engine
+        assert ctx.dim_theta <= eng.max_slots, "sharded prefill keeps one slot per dimension"
+        tags = eng.__dict__.setdefault("_slot_tags", {})
+        if all(tags.get(d) == (self._uid, ctx.key, d) for d in range(ctx.dim_theta)):
+            return self  # every slot is current: nothing to build or exchange
+        N = ctx.joint.shape[0]
+        for d in range(ctx.dim_theta):
+            if d % world == rank:
+                self._ensure_slot(ctx, d)
+        for d in range(ctx.dim_theta):
+            owner, F = d % world, ctx.dim_x + d
+            T = (F + 1) // 2 + 1
+            if owner == rank:
+                enc, borders, kv = eng.slot_pack(d)
+            else:
+                enc = torch.empty(eng.ENC_STATE_FLOATS, dtype=torch.float32, device=eng.device)
+                borders = torch.empty(eng.cfg.num_buckets + 1, dtype=torch.float32, device=eng.device)
+                kv = torch.empty(eng.cfg.nlayers, T, N, 64, dtype=torch.bfloat16, device=eng.device)
+            for t in (enc, borders, kv):
+                dist.broadcast(t, src=owner)
+            if owner != rank:
+                eng.slot_unpack(d, N, F, enc, borders, kv)
+                tags[d] = (self._uid, ctx.key, d)
+        return self
+
     def invalidate_cache(self):
         self._ctx = None
         self.engine.__dict__.pop("_slot_tags", None)
@@ -172,6 +210,8 @@ class NPE_PFN_Core:
         `uniforms[M, dim_theta]` may be injected (parity tests); otherwise Philox4x32-10 keyed by a seed taken
         from torch's global generator, counter = (row, dimension)."""
         ctx = self._prepare_context(x, use_filter)
+        if self.shard_prefill and use_filter:
+            self.prefill_sharded(x)
         eng = self.engine
         dev = eng.device
         dx, dth = ctx.dim_x, ctx.dim_theta
@@ -253,6 +293,8 @@ class NPE_PFN_Core:
                                  return_device: bool = False) -> Tensor:
         """sum_d log p(theta_d | x, theta_<d), teacher forced (npe_pfn.py:462-524); -inf -> log(eps) per dim."""
         ctx = self._prepare_context(x)
+        if self.shard_prefill:
+            self.prefill_sharded(x)
         eng = self.engine
         dev = eng.device
         dx, dth = ctx.dim_x, ctx.dim_theta

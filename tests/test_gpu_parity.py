@@ -247,6 +247,23 @@ def test_get_context_uses_device_filter(engine):
     assert torch.equal(th_d, th_h) and torch.equal(x_d, x_h)
 
 
+def test_slot_pack_unpack_roundtrip(engine):
+    """A slot exported with slot_pack and installed into another slot with slot_unpack (what ranks exchange in the
+    sharded prefill) answers exactly like the original."""
+    g = torch.Generator().manual_seed(77)
+    Xc, yc, Xt = torch.randn(90, 5, generator=g), torch.randn(90, generator=g), torch.randn(40, 5, generator=g)
+    engine.prefill(7, Xc, yc)
+    a = engine.forward_logits(7, Xt)
+    enc, borders, kv = engine.slot_pack(7)
+    engine.slot_unpack(8, 90, 5, enc, borders, kv)
+    b = engine.forward_logits(8, Xt)
+    assert torch.equal(a, b)
+    u = torch.rand(40, generator=g)
+    ta, _, _ = engine.head_sample(7, a, uniforms=u)
+    tb, _, _ = engine.head_sample(8, b, uniforms=u)
+    assert torch.equal(ta, tb) and engine.slot_info(8) == engine.slot_info(7)
+
+
 def test_accept_compact_matches_torch(engine):
     g = torch.Generator().manual_seed(3)
     for M, dim in [(1, 2), (255, 3), (256, 1), (100_003, 5)]:
