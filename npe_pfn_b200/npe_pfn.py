@@ -496,8 +496,12 @@ class DensityRatioWrapper:
     labels them 0 / 1 and fits the classifier; `ratio_log_probs` turns its class probabilities into a log density
     (points outside the box get the floor value log U + log(eps) - log(1 + eps))."""
 
+    #: estimator class behind the wrapper (tests substitute the CPU oracle's classifier to compare the wrapper's
+    #: logic with the reference's own DensityRatioWrapper)
+    classifier_cls = B200TabPFNClassifier
+
     def __init__(self, **init_kwargs):
-        self._classifier = B200TabPFNClassifier(**init_kwargs)
+        self._classifier = self.classifier_cls(**init_kwargs)
         self._key = None  # (x, x_context, theta_context, n, padding) of the current fit
         self._padded_dim_min = None
         self._padded_dim_max = None

@@ -77,3 +77,33 @@ def test_reference_public_api_shapes_over_oracle(ref_pkg):
     assert sb.shape == (3, 4, 2)
     with pytest.raises(ValueError):
         post.sample((2,), x[:2])
+
+
+def test_reference_density_ratio_wrapper_equals_mirror(ref_pkg):
+    """`DensityRatioWrapper` of the reference (npe_pfn.py:603-704) against the mirror in npe_pfn_b200, both over the
+    oracle classifier and the same posterior draws / torch seed: identical box, cache decisions and log-probs."""
+    pkg, core = ref_pkg
+    from npe_pfn_b200.npe_pfn import DensityRatioWrapper as Mirror
+    from oracle.classifier import OracleTabPFNClassifier
+
+    class MirrorOverOracle(Mirror):
+        classifier_cls = OracleTabPFNClassifier
+
+    g = torch.Generator().manual_seed(21)
+    draws = torch.randn(60, 2, generator=g) * torch.tensor([0.5, 2.0]) + 1.0
+    x, xc, tc = torch.randn(1, 3, generator=g), torch.randn(30, 3, generator=g), torch.randn(30, 2, generator=g)
+    th = torch.randn(25, 2, generator=g) * 2 + 1.0
+    th[0] = 50.0  # outside the padded box
+    ref, mine = core.DensityRatioWrapper(), MirrorOverOracle()
+    assert ref.refit_necessary(x, xc, tc, 60, 0.1) and mine.refit_necessary(x, xc, tc, 60, 0.1)
+    torch.manual_seed(5)
+    ref.fit(x, draws, 0.1, xc, tc)
+    torch.manual_seed(5)
+    mine.fit(x, draws, 0.1, xc, tc)
+    assert torch.equal(ref._padded_dim_min, mine._padded_dim_min) and torch.equal(ref._padded_dim_max, mine._padded_dim_max)
+    assert torch.equal(ref._uniform_log_prob, mine._uniform_log_prob)
+    for args in [(x, xc, tc, 60, 0.1), (x + 1, xc, tc, 60, 0.1), (x, xc[:-1], tc[:-1], 60, 0.1), (x, xc, tc, 61, 0.1),
+                 (x, xc, tc, 60, 0.2)]:
+        assert ref.refit_necessary(*args) == mine.refit_necessary(*args)
+    a, b = ref.ratio_log_probs(th, 1e-15), mine.ratio_log_probs(th, 1e-15)
+    assert torch.allclose(a, b, atol=1e-6) and torch.isfinite(a).all()
