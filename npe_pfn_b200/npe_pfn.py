@@ -328,10 +328,25 @@ class NPE_PFN_Core:
             return self._sample(batch_size, x, repeat_x=True, with_log_prob=with_log_prob, eps=eps,
                                 return_device=True)
 
+        num_samples = torch.Size(sample_shape).numel()
+        if self.prior is not None and self._bounds() == (None, None) and max_iter_rejection is None:
+            # the prior's support is all of R^d: every (finite) draw is accepted, so the rejection loop degenerates to
+            # ceil(S / max_sampling_batch_size) proposal rounds with nothing to compact and no host synchronisation
+            parts, lps = [], []
+            for i in range(0, num_samples, max_sampling_batch_size):
+                t, lp = proposal_fn(min(max_sampling_batch_size, num_samples - i))
+                parts.append(t)
+                lps.append(lp)
+            self.last_acceptance_rate = 1.0
+            samples = (torch.cat(parts) if len(parts) > 1 else parts[0]).cpu() if parts else torch.empty(0, 0)
+            if with_log_prob:
+                return samples, (torch.cat(lps) if len(lps) > 1 else lps[0]).cpu()
+            return samples
+
         samples, log_probs, _ar = accept_reject_sample(
             proposal=proposal_fn,
             accept_reject_fn=_SupportCheck(self),
-            num_samples=torch.Size(sample_shape).numel(),
+            num_samples=num_samples,
             show_progress_bars=self.show_progress_bars,
             max_sampling_batch_size=max_sampling_batch_size,
             proposal_sampling_kwargs={},

@@ -102,6 +102,21 @@ def main():
     out.append({"config": "bernoulli_glm sample_batched", "observations": n_obs, "samples_per_obs": n, "seconds": dt,
                 "samples_per_s": n_obs * n / dt})
 
+    # 5. sweep point: N = 50k context (beyond the 10k default), 2-D theta, log_prob of M rows (autoregressive)
+    g = torch.Generator().manual_seed(5)
+    N5, M5 = int(50_000 * min(a.scale, 1.0)), int(20_000 * a.scale)
+    theta = torch.randn(N5, 2, generator=g)
+    x = theta @ torch.randn(2, 10, generator=g) + 0.1 * torch.randn(N5, 10, generator=g) + 1.0
+    post = NPE_PFN_Core(prior=None).append_simulations(theta, x)
+    _, dt_pre = timed(lambda: post.prefill(x[:1]))
+    th = torch.randn(M5, 2, generator=g)
+    lp, dt = timed(lambda: post.log_prob(th, x[:1], max_sampling_batch_size=M5))
+    assert lp.shape == (M5,) and torch.isfinite(lp).all()
+    info = post.engine.slot_info(1)
+    out.append({"config": "sweep N=50k context", "context_rows": N5, "prefill_seconds": dt_pre, "rows": M5, "seconds": dt,
+                "rows_per_s": M5 / dt, "kv_cache_MB_dim1": info["kv_bytes"] / 1e6,
+                "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9})
+
     for o in out:
         print(json.dumps(o))
 
