@@ -41,6 +41,8 @@ struct TcArgs {
     int heads, n_qtiles;     // work item = (column t, query tile, head): item = (t * n_qtiles + qt) * heads + h
     int64_t items;
     uint32_t wait_ticks;     // suspend-time hint of the producer / MMA threads' barrier waits (0 = none)
+    uint32_t stagger_ns;     // persistent mode: residency slot k (blockIdx / #SMs) starts k * stagger_ns later
+    uint32_t num_sms;
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -204,6 +206,10 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     const uint32_t tmem = tmem_slot_ptr[0];     // S/P double buffer
     const uint32_t tmem_o = tmem_slot_ptr[1];   // O accumulator
 
+    if (p.stagger_ns) {  // de-phase the CTAs that share an SM (they would otherwise run their tiles in lockstep)
+        const uint32_t slot = blockIdx.x / p.num_sms;
+        if (slot) __nanosleep(slot * p.stagger_ns);
+    }
     // Persistent: every role walks the same sequence of work items; barrier phases are carried across items through
     // running counters (g = key tiles processed so far, qn = items processed so far).
     if (warp == 4) {
@@ -452,7 +458,7 @@ static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUten
 }
 
 static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, int poly_mod, int num_sms, int persist,
-                                         uint32_t wait_ticks, cudaStream_t st) {
+                                         uint32_t wait_ticks, uint32_t stagger_ns, cudaStream_t st) {
     CUtensorMap mq, mkv;
     TcArgs p{};
     p.O = a.O; p.o_row = a.o_row; p.o_tok = a.o_tok; p.R = a.R; p.N = a.N;
@@ -478,6 +484,8 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, in
     p.n_qtiles = (int)ceil_div(a.R, TC_BM);
     p.items = (int64_t)T * p.n_qtiles * heads;
     p.wait_ticks = wait_ticks;
+    p.stagger_ns = persist ? stagger_ns : 0;
+    p.num_sms = (uint32_t)num_sms;
     // persist: 3 CTAs per SM walk the items; otherwise one CTA per item (the hardware scheduler staggers them)
     dim3 grid((unsigned)(persist ? std::min<int64_t>(p.items, 3 * (int64_t)num_sms) : p.items));
     switch (poly_mod) {

@@ -88,6 +88,7 @@ struct pfn_ctx {
     int gemm_impl = 1;  // 0 = mma.sync, 1 = tcgen05
     int attn_persist = 0;       // 1: persistent item-attention CTAs (3 per SM)
     int attn_wait_ticks = 1000;
+    int attn_stagger_ns = 0;
     int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
     int attn_poly = 0;  // one pair of every k pairs of exponentials on the FMA pipes (0 = all on MUFU; r1 sweep: no gain)
     int num_sms = 148;
@@ -193,7 +194,7 @@ int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
     TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
 #ifdef PFN_WITH_ATTN_TC
     if (c->attn_impl == 1) {
-        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly, c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, st));
+        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly, c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns, st));
     } else
 #endif
     {
@@ -438,6 +439,7 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "standardize_y")) { c->standardize_y = (int)value; return 0; }
     if (!strcmp(key, "attn_persist")) { c->attn_persist = (int)value; return 0; }
     if (!strcmp(key, "attn_wait_ticks")) { c->attn_wait_ticks = (int)value; return 0; }
+    if (!strcmp(key, "attn_stagger_ns")) { c->attn_stagger_ns = (int)value; return 0; }
     if (!strcmp(key, "attn_poly")) {
         PFN_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4 || value == 6 || value == 8, "attn_poly must be 0,2,3,4,6,8");
         c->attn_poly = (int)value;
