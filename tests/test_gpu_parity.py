@@ -247,6 +247,23 @@ def test_get_context_uses_device_filter(engine):
     assert torch.equal(th_d, th_h) and torch.equal(x_d, x_h)
 
 
+def test_empty_inputs(engine):
+    """Zero test rows / zero candidates are valid calls through the C-ABI and return empty results."""
+    g = torch.Generator().manual_seed(4)
+    engine.prefill(9, torch.randn(20, 3, generator=g), torch.randn(20, generator=g))
+    assert engine.forward_logits(9, torch.empty(0, 3)).shape[0] == 0
+    joint = torch.empty(0, 5, device="cuda")
+    engine.sample_step(9, joint, 3, 3, seed=1)
+    lp = torch.empty(0, device="cuda")
+    engine.logprob_step(9, joint, 3, 3, lp)
+    th, bins, _ = engine.head_sample(9, torch.empty(0, 5000, device="cuda"), return_bins=True)
+    assert th.shape == (0,) and bins.shape == (0,)
+    with pytest.raises(RuntimeError):
+        engine.forward_logits(10, torch.randn(2, 3))  # slot never prefilled
+    with pytest.raises(RuntimeError):
+        engine.prefill(9, torch.randn(4, 200), torch.randn(4))  # more features than the model supports
+
+
 def test_slot_pack_unpack_roundtrip(engine):
     """A slot exported with slot_pack and installed into another slot with slot_unpack (what ranks exchange in the
     sharded prefill) answers exactly like the original."""
@@ -308,6 +325,37 @@ def test_rows_independent_and_chunk_invariant(engine):
         engine.set_option("chunk_rows", 0)
     assert torch.equal(a, c)
     assert torch.isfinite(a).all()
+
+
+def test_full_size_properties(engine):
+    """BASELINE config 2 sizes (10-D theta / 10-D x, 10 000 simulations, 20 000 draws): properties that do not need
+    the (slow) oracle - determinism under a seed, invariance to the chunking of test rows, and the round trip
+    sample -> log_prob: the log density accumulated while sampling equals log_prob of the same draws."""
+    from npe_pfn_b200 import NPE_PFN_Core
+    g = torch.Generator().manual_seed(2024)
+    N, d, S = 10_000, 10, 20_000
+    theta = math.sqrt(0.1) * torch.randn(N, d, generator=g)
+    x = theta + math.sqrt(0.1) * torch.randn(N, d, generator=g)
+    xo = x[:1].clone()
+    prior = torch.distributions.MultivariateNormal(torch.zeros(d), 0.1 * torch.eye(d))
+    post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    s1, lp1 = post._sample(S, xo, with_log_prob=True, seed=123)
+    s2, lp2 = post._sample(S, xo, with_log_prob=True, seed=123)
+    assert torch.equal(s1, s2) and torch.equal(lp1, lp2)
+    assert s1.shape == (S, d) and torch.isfinite(s1).all() and torch.isfinite(lp1).all()
+    engine.set_option("chunk_rows", 6000)
+    try:
+        s3, lp3 = post._sample(S, xo, with_log_prob=True, seed=123)
+    finally:
+        engine.set_option("chunk_rows", 0)
+    assert torch.equal(s1, s3) and torch.equal(lp1, lp3)
+    s4, _ = post._sample(S, xo, seed=124)
+    assert not torch.equal(s1, s4)
+    lp = post.log_prob(s1, xo, max_sampling_batch_size=S)
+    assert (lp - lp1).abs().max() <= 1e-3
+    # draws live inside the bucket range spanned by the simulations (borders are renormalised per dimension)
+    assert float(s1.abs().max()) < 10.0
+    assert post.engine.slot_info(9)["N"] == N and post.engine.slot_info(9)["T"] == 11
 
 
 def test_item_attention_impls_agree(engine):
