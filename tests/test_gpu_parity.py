@@ -509,6 +509,25 @@ def test_classifier_and_ratio_log_prob(engine, weights):
     assert wrapper.refit_necessary(x[1:2], *reversed(post.get_context(x[1:2])), 200, 0.1)
 
 
+@pytest.mark.parametrize("num_clusters", [1, 3])
+def test_unconditional_estimator(engine, num_clusters):
+    """TabPFN_Based_Uncond_Estimator (npe_pfn.py:747-900; shapes / finiteness as tests/test_npe_pfn.py:292-317)."""
+    from npe_pfn_b200 import TabPFN_Based_Uncond_Estimator
+    torch.manual_seed(0)
+    theta = torch.cat([torch.randn(60, 2) * 0.3 + c for c in (-2.0, 0.0, 2.0)])
+    est = TabPFN_Based_Uncond_Estimator(num_clusters=num_clusters, regressor_init_kwargs={"engine": engine})
+    est.append_simulations(theta)
+    s = est.sample((50,))
+    assert s.shape == (50, 2) and torch.isfinite(s).all()
+    s2, lp2 = est.sample((20,), with_log_prob=True)
+    assert s2.shape == (20, 2) and lp2.shape == (20,) and torch.isfinite(lp2).all()
+    lp = est.log_prob(s)
+    assert lp.shape == (50,) and torch.isfinite(lp).all()
+    assert est.cluster_state == 0
+    with pytest.raises(ValueError):
+        est.log_prob(s, mode="bogus")
+
+
 def test_tsnpe_rounds_ratio_based(engine):
     """run_tsnpe_pfn with its default log_prob_mode ("ratio_based", tsnpe_pfn.py:25): classifier bounds drive
     prereject_with_bounds in the support proposal."""
