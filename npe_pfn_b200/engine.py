@@ -212,14 +212,21 @@ class Engine:
                                              int(accumulate), self._stream()))
         return out_theta, bins, out_logp
 
-    def head_nll(self, slot: int, logits: torch.Tensor, y: torch.Tensor, eps=1e-15):
+    def head_nll(self, slot: int, logits: torch.Tensor, y: torch.Tensor, eps=1e-15, ld_y: int = 1, out_logp=None,
+                 accumulate=False):
+        """-log p(y_r) for logits [M, B], or one logits row evaluated against all M targets (logits.shape[0] == 1).
+        With `out_logp` the clamped log-prob (-inf -> log eps) is written / accumulated there instead."""
         logits = logits.to(self.device, torch.float32)
-        y = y.to(self.device, torch.float32).contiguous()
-        M = logits.shape[0]
-        out = torch.empty(M, dtype=torch.float32, device=self.device)
-        self._check(self.lib.pfn_head_nll(self._h, slot, _ptr(logits), logits.stride(0), M, _ptr(y), 1, _ptr(out), None,
-                                          eps, 0, self._stream()))
-        return out
+        y = y.to(self.device, torch.float32)
+        if ld_y == 1:
+            y = y.reshape(-1).contiguous()
+        M = y.shape[0] if y.ndim == 1 else y.numel()
+        ld = 0 if (logits.shape[0] == 1 and M != 1) else logits.stride(0)
+        assert logits.shape[0] in (1, M)
+        out = None if out_logp is not None else torch.empty(M, dtype=torch.float32, device=self.device)
+        self._check(self.lib.pfn_head_nll(self._h, slot, _ptr(logits), ld, M, _ptr(y), ld_y, _ptr(out), _ptr(out_logp), eps,
+                                          int(accumulate), self._stream()))
+        return out if out_logp is None else out_logp
 
     def sample_step(self, slot: int, joint: torch.Tensor, n_features: int, out_col: int, uniforms=None, seed=0, row0=0,
                     offset=0, out_logp=None, eps=1e-15, accumulate=True, bins=None):

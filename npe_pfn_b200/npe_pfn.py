@@ -308,7 +308,12 @@ class NPE_PFN_Core:
         lp = torch.zeros(m, dtype=torch.float32, device=dev)
         for d in range(dth):
             slot = self._ensure_slot(ctx, d)
-            eng.logprob_step(slot, buf, dx + d, dx + d, lp, eps=eps, accumulate=True)
+            if d == 0 and repeat_x and m > 1 and xd.shape[0] == 1:
+                # one observation: dimension 0 sees identical features in every row -> one forward row, m targets
+                logits = eng.forward_logits(slot, buf[:1, :dx])
+                eng.head_nll(slot, logits, buf[:, dx], eps=eps, ld_y=buf.stride(0), out_logp=lp, accumulate=True)
+            else:
+                eng.logprob_step(slot, buf, dx + d, dx + d, lp, eps=eps, accumulate=True)
         return lp if return_device else lp.cpu()
 
     # -- public API -----------------------------------------------------------------------------------------
