@@ -23,14 +23,21 @@
 
 namespace pfn {
 
-constexpr int TC_BM = 128, TC_BN = 64, TC_STAGES = 7, TC_THREADS = 192;
+#ifndef PFN_ATTN_BN
+#define PFN_ATTN_BN 64   // keys per tile (64 or 32)
+#endif
+#ifndef PFN_ATTN_CTAS
+#define PFN_ATTN_CTAS 3  // resident CTAs per SM the kernel is compiled for
+#endif
+constexpr int TC_BM = 128, TC_BN = PFN_ATTN_BN, TC_STAGES = TC_BN == 64 ? 7 : 8, TC_THREADS = 192;
+static_assert(TC_BN == 64 || TC_BN == 32, "key tile must be 32 or 64");
 constexpr int TC_Q_BYTES = TC_BM * kDh * 2;           // 8 KB: 128 rows x 64 B
 constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 4 KB: 64 keys x 64 B
 constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // K tile + V tile
 // 66 816 B: three CTAs per SM fit in shared memory (200 KB), a fourth does not.  TMEM: each CTA takes 128 columns
 // (S0/P0 [0,64), S1/P1 [64,128)) plus a separate 32-column allocation for O: 3 x 160 = 480 of the 512 columns.
 constexpr int TC_SMEM_BYTES = 1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256;
-constexpr int TC_TMEM_COLS_S = 128, TC_TMEM_COLS_O = 32;
+constexpr int TC_TMEM_COLS_S = 2 * TC_BN, TC_TMEM_COLS_O = 32;
 
 struct TcArgs {
     bf16* O;
@@ -120,6 +127,13 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
         "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
         "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31]) : "memory");
 }
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
 __device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
@@ -154,7 +168,7 @@ __device__ __forceinline__ float exp2_poly(float x) {
 
 // POLY_MOD = 0: every exponential on MUFU; k > 0: one pair of every k pairs uses exp2_poly
 template <int POLY_MOD>
-__global__ void __launch_bounds__(TC_THREADS, 3)
+__global__ void __launch_bounds__(TC_THREADS, PFN_ATTN_CTAS)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs p) {
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
@@ -300,25 +314,32 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const uint32_t scol = trow + b * TC_BN;
                 mbar_wait(bar_s + 8 * b, (g >> 1) & 1u);
                 tc_fence_after();
-                // pass 1: both 32-column halves -> tile maximum (the second half is re-read later instead of being
-                // kept live, so the kernel fits the 112 registers that three CTAs per SM allow)
-                uint32_t sa[32], sb[32];
+                // pass 1: the tile's 32-column pieces -> tile maximum (with 64-key tiles the second piece is re-read
+                // later instead of being kept live, so the kernel fits the register budget of 3 CTAs per SM)
+                constexpr bool kTwo = TC_BN == 64;
+                uint32_t sa[32], sb[kTwo ? 32 : 1];
                 tmem_ld32(scol, sa);
-                tmem_ld32(scol + 32, sb);
+                if constexpr (kTwo) tmem_ld32(scol + 32, sb);
                 tmem_wait_ld();
                 const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
                 if (nvalid < TC_BN) {
 #pragma unroll
                     for (int i = 0; i < 32; ++i) {
                         if (i >= nvalid) sa[i] = 0xff800000u;  // -inf
-                        if (32 + i >= nvalid) sb[i] = 0xff800000u;
+                        if constexpr (kTwo)
+                            if (32 + i >= nvalid) sb[i] = 0xff800000u;
                     }
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
                 for (int i = 0; i < 32; ++i) {
-                    mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
-                    mx1 = fmaxf(mx1, __uint_as_float(sb[i]));
+                    if constexpr (kTwo) {
+                        mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
+                        mx1 = fmaxf(mx1, __uint_as_float(sb[i]));
+                    } else {
+                        if (i & 1) mx1 = fmaxf(mx1, __uint_as_float(sa[i]));
+                        else mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
+                    }
                 }
                 const float mt = fmaxf(mx0, mx1) * sc;
                 if (j == 0) {
@@ -341,8 +362,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         tmem_st32(orow, ov);
                     }
                 }
-                // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs; first half from registers, second half re-read
-                uint32_t pk[32];
+                // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs
+                uint32_t pk[kTwo ? 32 : 16];
 #pragma unroll
                 for (int i = 0; i < 16; ++i) {
                     const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
@@ -354,25 +375,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                     l1 += p1;
                     pk[i] = pack_bf16x2(p0, p1);
                 }
-                tmem_ld32(scol + 32, sa);
-                tmem_wait_ld();
-                if (nvalid < TC_BN) {
+                if constexpr (kTwo) {
+                    tmem_ld32(scol + 32, sa);
+                    tmem_wait_ld();
+                    if (nvalid < TC_BN) {
 #pragma unroll
-                    for (int i = 0; i < 32; ++i)
-                        if (32 + i >= nvalid) sa[i] = 0xff800000u;
-                }
+                        for (int i = 0; i < 32; ++i)
+                            if (32 + i >= nvalid) sa[i] = 0xff800000u;
+                    }
 #pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
-                    const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
-                    const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
-                    const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
-                    const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
-                    l0 += p0;
-                    l1 += p1;
-                    pk[16 + i] = pack_bf16x2(p0, p1);
+                    for (int i = 0; i < 16; ++i) {
+                        const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
+                        const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
+                        const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
+                        const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
+                        const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
+                        l0 += p0;
+                        l1 += p1;
+                        pk[16 + i] = pack_bf16x2(p0, p1);
+                    }
+                    tmem_st32(scol, reinterpret_cast<uint32_t(&)[32]>(pk));
+                } else {
+                    tmem_st16(scol, pk);
                 }
-                tmem_st32(scol, pk);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_p + 8 * b);

@@ -43,8 +43,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = _build.LIB_PATH
-    if build_if_missing and _build.is_stale():
+    path = os.environ.get("NPE_PFN_B200_LIB") or _build.LIB_PATH  # override: experimental builds (tuning sweeps)
+    if path == _build.LIB_PATH and build_if_missing and _build.is_stale():
         try:
             _build.build_library()
         except Exception as e:  # stale-but-present library is still usable; missing one is fatal
