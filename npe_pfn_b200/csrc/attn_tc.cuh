@@ -153,21 +153,92 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_ma
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-// exp2 on the FMA / ALU pipes (no MUFU): Cody-Waite split x = n + f, f in [-0.5, 0.5], degree-3 minimax
-// polynomial for 2^f (max relative error 7.7e-5, P is rounded to bf16 = 3.9e-3 anyway), exponent re-inserted
-// with one integer shift-add.  Used for a fraction of the elements so MUFU and FMA pipes work in parallel.
-__device__ __forceinline__ float exp2_poly(float x) {
-    x = fmaxf(x, -126.0f);
-    const float t = __fadd_rn(x, 12582912.0f);  // 1.5 * 2^23: the low mantissa bits now hold round(x)
-    const float f = __fsub_rn(x, __fsub_rn(t, 12582912.0f));
-    float p = __fmaf_rn(0.05508868396282196f, f, 0.24260404706001282f);
-    p = __fmaf_rn(p, f, 0.6932762265205383f);
-    p = __fmaf_rn(p, f, 0.9999289512634277f);
-    return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
+// ---- packed fp32x2 arithmetic (sm_100: FFMA2 / FADD2 do two lanes per issue slot) and the 3-input maximum ----
+__device__ __forceinline__ uint64_t pk2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t ffma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t fadd2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ float fmax3(float a, float b, float c) {
+    float d;
+    asm("max.f32 %0, %1, %2, %3;" : "=f"(d) : "f"(a), "f"(b), "f"(c));
+    return d;
 }
 
-// POLY_MOD = 0: every exponential on MUFU; k > 0: one pair of every k pairs uses exp2_poly
-template <int POLY_MOD>
+constexpr float kExpMagic = 12582912.0f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+
+// P = 2^(S * sc - m) for one 32-column piece of a score tile, as 16 bf16 pairs, row sum accumulated in l2 (two lanes).
+// The reference maximum m is INTEGER valued (see the caller), so both forms below are exact in their argument:
+//   MUFU pair:  x = fma(S, sc, -m) (one FFMA2), two ex2.approx;
+//   FMA pair:   Cody-Waite on the FMA pipes, two lanes per instruction.  With C = magic - m (an exact integer),
+//               t = fma(S, sc, C) = magic + n, n = round(S sc - m);  w = C - t = -(m + n) exactly;
+//               f = fma(S, sc, w) in [-0.5, 0.5];  2^f by a minimax polynomial (degree 3: 7.5e-5, degree 2: 1.7e-3
+//               relative; P is rounded to bf16 = 3.9e-3 afterwards);  the exponent n is added with one integer
+//               shift-add per lane ((magic + n) << 23 = n << 23 mod 2^32).  S is clamped below at smin so that
+//               n >= -125 (also maps the -inf of masked keys to 2^-125 ~ 0).
+// POLY16 of every 16 pairs take the FMA form, spread evenly, so the MUFU pipe (16 ex2 / clk / SM, the bound of
+// this kernel) and the FMA pipes work side by side.
+// `between(i)` runs after pair i: the caller's hook for work that should be interleaved with the exponentials (the
+// maximum pass over the NEXT piece, the wait for its TMEM load).
+template <int POLY16, int DEG, typename Between>
+__device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t* pk, float sc, float neg_m, float cm,
+                                              float smin, uint64_t& l2, Between between) {
+    const uint64_t SC = pk2(sc, sc), NM = pk2(neg_m, neg_m), CM = pk2(cm, cm), NEG1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool poly = ((i + 1) * POLY16) / 16 != (i * POLY16) / 16;
+        float p0, p1;
+        if (!poly) {
+            float x0, x1;
+            upk2(ffma2(pk2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1])), SC, NM), x0, x1);
+            p0 = fast_exp2(x0);
+            p1 = fast_exp2(x1);
+        } else {
+            const uint64_t S2 = pk2(fmaxf(__uint_as_float(s[2 * i]), smin), fmaxf(__uint_as_float(s[2 * i + 1]), smin));
+            const uint64_t t2 = ffma2(S2, SC, CM);
+            const uint64_t w2 = ffma2(t2, NEG1, CM);
+            const uint64_t f2 = ffma2(S2, SC, w2);
+            uint64_t q2;
+            if (DEG == 2) {
+                q2 = ffma2(pk2(0.23842893540859222f, 0.23842893540859222f), f2, pk2(0.7034479975700378f, 0.7034479975700378f));
+                q2 = ffma2(q2, f2, pk2(1.0004431009292603f, 1.0004431009292603f));
+            } else {
+                q2 = ffma2(pk2(0.05517163127660751f, 0.05517163127660751f), f2, pk2(0.2426111251115799f, 0.2426111251115799f));
+                q2 = ffma2(q2, f2, pk2(0.6932609677314758f, 0.6932609677314758f));
+                q2 = ffma2(q2, f2, pk2(0.9999280571937561f, 0.9999280571937561f));
+            }
+            float q0, q1, t0, t1;
+            upk2(q2, q0, q1);
+            upk2(t2, t0, t1);
+            p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+            p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+        }
+        l2 = fadd2(l2, pk2(p0, p1));
+        pk[i] = pack_bf16x2(p0, p1);
+        between(i);
+    }
+}
+template <int POLY16, int DEG>
+__device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t* pk, float sc, float neg_m, float cm,
+                                              float smin, uint64_t& l2) {
+    softmax_exp32<POLY16, DEG>(s, pk, sc, neg_m, cm, smin, l2, [](int) {});
+}
+
+// POLY16 = 0: every exponential on MUFU; k > 0: k of every 16 pairs on the FMA pipes (softmax_exp32)
+template <int POLY16, int DEG>
 __global__ void __launch_bounds__(TC_THREADS, PFN_ATTN_CTAS)
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs p) {
     extern __shared__ uint8_t tc_smem_raw[];
@@ -308,7 +379,9 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             const int t = (int)(item / per_col), rem = (int)(item % per_col);
             const int qt = rem / p.heads, h = rem % p.heads;
             const int64_t m0 = (int64_t)qt * TC_BM;
-            float m_ref = -INFINITY, l0 = 0.f, l1 = 0.f;
+            // m_ref: integer-valued reference maximum (scaled units); cm = magic - m_ref; smin: score clamp of the FMA form
+            float m_ref = -INFINITY, cm = 0.f, smin = 0.f;
+            uint64_t l2 = 0;
             for (int j = 0; j < ntiles; ++j, ++g) {
                 const uint32_t b = g & 1u;
                 const uint32_t scol = trow + b * TC_BN;
@@ -332,26 +405,33 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 float mx0 = -INFINITY, mx1 = -INFINITY;
 #pragma unroll
-                for (int i = 0; i < 32; ++i) {
+                for (int i = 0; i < 16; ++i) {
                     if constexpr (kTwo) {
-                        mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
-                        mx1 = fmaxf(mx1, __uint_as_float(sb[i]));
+                        mx0 = fmax3(mx0, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
+                        mx1 = fmax3(mx1, __uint_as_float(sb[2 * i]), __uint_as_float(sb[2 * i + 1]));
                     } else {
-                        if (i & 1) mx1 = fmaxf(mx1, __uint_as_float(sa[i]));
-                        else mx0 = fmaxf(mx0, __uint_as_float(sa[i]));
+                        if (i & 1) mx1 = fmax3(mx1, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
+                        else mx0 = fmax3(mx0, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
                     }
                 }
                 const float mt = fmaxf(mx0, mx1) * sc;
-                if (j == 0) {
-                    m_ref = mt;
-                } else {
-                    // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
-                    const bool need = mt > m_ref + 8.0f;
-                    if (__any_sync(0xffffffffu, need)) {
-                        const float corr = need ? fast_exp2(m_ref - mt) : 1.0f;
-                        if (need) m_ref = mt;
-                        l0 *= corr;
-                        l1 *= corr;
+                // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
+                const bool need = (j == 0) || (mt > m_ref + 8.0f);
+                if (__any_sync(0xffffffffu, need)) {
+                    float corr = 1.0f;
+                    if (need) {
+                        const float m_new = rintf(mt);
+                        if (j > 0) {
+                            corr = fast_exp2(m_ref - m_new);
+                            float l0, l1;
+                            upk2(l2, l0, l1);
+                            l2 = pk2(l0 * corr, l1 * corr);
+                        }
+                        m_ref = m_new;
+                        cm = kExpMagic - m_ref;
+                        smin = (m_ref - 125.0f) * (1.0f / sc);
+                    }
+                    if (j > 0) {
                         mbar_wait(bar_pv, (g - 1u) & 1u);  // O += P_{j-1} V_{j-1} must have landed
                         tc_fence_after();
                         uint32_t ov[32];
@@ -364,17 +444,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 }
                 // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs
                 uint32_t pk[kTwo ? 32 : 16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
-                    const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
-                    const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
-                    const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
-                    const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
-                    l0 += p0;
-                    l1 += p1;
-                    pk[i] = pack_bf16x2(p0, p1);
-                }
+                softmax_exp32<POLY16, DEG>(sa, pk, sc, -m_ref, cm, smin, l2);
                 if constexpr (kTwo) {
                     tmem_ld32(scol + 32, sa);
                     tmem_wait_ld();
@@ -383,17 +453,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         for (int i = 0; i < 32; ++i)
                             if (32 + i >= nvalid) sa[i] = 0xff800000u;
                     }
-#pragma unroll
-                    for (int i = 0; i < 16; ++i) {
-                        const float x0 = fmaf(__uint_as_float(sa[2 * i]), sc, -m_ref);
-                        const float x1 = fmaf(__uint_as_float(sa[2 * i + 1]), sc, -m_ref);
-                        const bool poly = POLY_MOD > 0 && (i % (POLY_MOD > 0 ? POLY_MOD : 1)) == (POLY_MOD - 1);
-                        const float p0 = poly ? exp2_poly(x0) : fast_exp2(x0);
-                        const float p1 = poly ? exp2_poly(x1) : fast_exp2(x1);
-                        l0 += p0;
-                        l1 += p1;
-                        pk[16 + i] = pack_bf16x2(p0, p1);
-                    }
+                    softmax_exp32<POLY16, DEG>(sa, pk + 16, sc, -m_ref, cm, smin, l2);
                     tmem_st32(scol, reinterpret_cast<uint32_t(&)[32]>(pk));
                 } else {
                     tmem_st16(scol, pk);
@@ -410,6 +470,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             tmem_wait_ld();
             const int64_t r = m0 + warp * 32 + lane;
             if (r < p.R) {
+                float l0, l1;
+                upk2(l2, l0, l1);
                 const float inv = 1.0f / (l0 + l1);
                 uint4* dst = reinterpret_cast<uint4*>(p.O + r * p.o_row + (int64_t)t * p.o_tok + h * kDh);
 #pragma unroll
@@ -465,7 +527,7 @@ static inline bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int POLY_MOD>
+template <int POLY16, int DEG>
 static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUtensorMap& mkv, const TcArgs& p, dim3 grid,
                                               cudaStream_t st) {
     static bool configured_dev[64] = {};  // the attribute is per device
@@ -473,12 +535,12 @@ static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUten
     cudaGetDevice(&dev);
     bool& configured = configured_dev[dev & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<POLY_MOD>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<POLY16, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    attn_tc_kernel<POLY_MOD><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
+    attn_tc_kernel<POLY16, DEG><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
     return cudaGetLastError();
 }
 
@@ -513,15 +575,16 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, in
     p.num_sms = (uint32_t)num_sms;
     // persist: 3 CTAs per SM walk the items; otherwise one CTA per item (the hardware scheduler staggers them)
     dim3 grid((unsigned)(persist ? std::min<int64_t>(p.items, 3 * (int64_t)num_sms) : p.items));
+    // poly_mod = k + 100 * (degree == 2): k of every 16 exponential pairs on the FMA pipes
+#define PFN_ATTN_CASE(K)                                                      \
+    case K: return launch_attn_tc_impl<K, 3>(mq, mkv, p, grid, st);           \
+    case 100 + K: return launch_attn_tc_impl<K, 2>(mq, mkv, p, grid, st);
     switch (poly_mod) {
-        case 0: return launch_attn_tc_impl<0>(mq, mkv, p, grid, st);
-        case 2: return launch_attn_tc_impl<2>(mq, mkv, p, grid, st);
-        case 3: return launch_attn_tc_impl<3>(mq, mkv, p, grid, st);
-        case 4: return launch_attn_tc_impl<4>(mq, mkv, p, grid, st);
-        case 6: return launch_attn_tc_impl<6>(mq, mkv, p, grid, st);
-        case 8: return launch_attn_tc_impl<8>(mq, mkv, p, grid, st);
+        case 0: return launch_attn_tc_impl<0, 3>(mq, mkv, p, grid, st);
+        PFN_ATTN_CASE(4) PFN_ATTN_CASE(5) PFN_ATTN_CASE(6) PFN_ATTN_CASE(7) PFN_ATTN_CASE(8) PFN_ATTN_CASE(10)
         default: return cudaErrorInvalidValue;
     }
+#undef PFN_ATTN_CASE
 }
 
 }  // namespace pfn

@@ -90,7 +90,7 @@ struct pfn_ctx {
     int attn_wait_ticks = 1000;
     int attn_stagger_ns = 0;
     int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
-    int attn_poly = 0;  // one pair of every k pairs of exponentials on the FMA pipes (0 = all on MUFU; r1 sweep: no gain)
+    int attn_poly = 5;  // k of every 16 pairs of exponentials on the FMA pipes (+100: degree-2 polynomial); 0 = all on MUFU. r1 sweep: 0 -> 437, 5 -> 473 TFLOP/s
     int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
     int time_kernels = 0;
@@ -396,6 +396,9 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
     }
     if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
     if (const char* e = getenv("NPE_PFN_B200_GEMM")) c->gemm_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
+    if (const char* e = getenv("NPE_PFN_B200_ATTN_POLY")) {  // tuning / parity sweeps of the exponential split
+        if (int rc = pfn_set_option(c, "attn_poly", atoll(e))) { delete c; return rc; }
+    }
     PFN_CUDA_OK(cudaMalloc(&c->wf, n_floats * 4));
     PFN_CUDA_OK(cudaMalloc(&c->wb, n_floats * 2));
     PFN_CUDA_OK(cudaMemcpyAsync(c->wf, weights, n_floats * 4, cudaMemcpyDeviceToDevice, st));
@@ -441,7 +444,9 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_wait_ticks")) { c->attn_wait_ticks = (int)value; return 0; }
     if (!strcmp(key, "attn_stagger_ns")) { c->attn_stagger_ns = (int)value; return 0; }
     if (!strcmp(key, "attn_poly")) {
-        PFN_REQUIRE(value == 0 || value == 2 || value == 3 || value == 4 || value == 6 || value == 8, "attn_poly must be 0,2,3,4,6,8");
+        const int64_t k = value % 100;
+        PFN_REQUIRE(value >= 0 && value < 200 && (value == 0 || k == 4 || k == 5 || k == 6 || k == 7 || k == 8 || k == 10),
+                    "attn_poly must be 0 or k (+100 for the degree-2 polynomial), k in 4,5,6,7,8,10");
         c->attn_poly = (int)value;
         return 0;
     }
