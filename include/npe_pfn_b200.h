@@ -65,7 +65,7 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
 int pfn_ctx_destroy(pfn_ctx* ctx);
 /* runtime switches (no reference counterpart): "attn_impl" / "gemm_impl" 0 = warp-level mma.sync kernels,
  * 1 = tcgen05/TMEM/TMA kernels (default); "chunk_rows" = test rows per pass; "standardize_y" 0 = targets enter the y-encoder unscaled (classifier head:
- * class indices, npe_pfn.py:610, 661); "attn_poly" k = one of every k pairs of softmax exponentials on the FMA pipes; "time_kernels" 1 = record a
+ * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes (+100: degree-2 polynomial); "time_kernels" 1 = record a
  * CUDA event pair around every attention / GEMM launch on its stream (read back with pfn_kernel_times). */
 int pfn_set_option(pfn_ctx* ctx, const char* key, int64_t value);
 
@@ -142,6 +142,39 @@ int pfn_slot_import(pfn_ctx* ctx, int slot, int64_t N, int F, const float* enc_s
                     const void* kv, void* stream);
 /* debug / parity: final-layer states of the last forward chunk [rows, T, E] fp32 */
 int pfn_debug_last_states(pfn_ctx* ctx, float* out, int64_t max_floats, void* stream);
+
+/* ---- ensemble path (n_estimators > 1): what upstream `TabPFNRegressor()` does by default for the reference's
+ * constructor call (npe_pfn.py:48; 8 members).  Each member is an ordinary slot (its own
+ * transformed context); these two calls are the per-member feature pipeline of the TEST rows and the combination of
+ * the members' logits.  All pointers inside the descriptor are DEVICE pointers owned by the caller. */
+typedef struct pfn_member_desc {
+    int32_t n_features_in;      /* raw feature count F of the rows handed in                                      */
+    int32_t n_keep;             /* non-constant raw features                                                      */
+    const int32_t* keep;        /* [n_keep] raw column indices                                                    */
+    int32_t kind;               /* 0: quantile-uniform + original columns (+ SVD components); 1: standardise ->   */
+                                /*    Yeo-Johnson -> standardise ("safepower")                                    */
+    int32_t n_quantiles;        /* kind 0                                                                         */
+    const float* quantiles;     /* kind 0: [n_keep][n_quantiles] ascending (references are j / (n_quantiles - 1)) */
+    const float* safepower;     /* kind 1: [5][n_keep] = in_mean | 1/in_std | lambda | out_mean | 1/out_std       */
+    int32_t svd_k;              /* kind 0: appended components (0 = none)                                         */
+    const float* svd_inv_scale; /* [2 n_keep]                                                                     */
+    const float* svd_vt;        /* [svd_k][2 n_keep]                                                              */
+    int32_t fingerprint;        /* append the row-hash feature                                                    */
+    int32_t n_out;              /* columns written = elementwise + svd_k + fingerprint                            */
+    const int32_t* perm;        /* [n_out] feature shuffle: out column c = pre-shuffle column perm[c]             */
+} pfn_member_desc;
+/* X[M, n_features_in] (row stride ldx) -> out[M, n_out] (row stride ld_out). */
+int pfn_member_transform(pfn_ctx* ctx, const pfn_member_desc* desc, const float* X, int64_t ldx, int64_t M, float* out,
+                         int64_t ld_out, void* stream);
+/* out[r, :] = log(mean_e probs_e[r, :]) on the common bucket borders.  Member e's logits for row r start at
+ * logits + e * member_stride + r * ld_logits (already divided by the temperature, as pfn_forward_logits returns them).
+ * idx[e][0] < 0: member e lives on the common borders (softmax only); otherwise its softmax masses (buckets with
+ * valid[e][j] == 0 dropped, renormalised) are re-binned: CDF_e(z_k) = C_e[idx[e][k]] + p_e[idx[e][k]] * frac[e][k] for the
+ * B + 1 common borders z_k, C_e the exclusive prefix sum, new mass k = max(CDF_e(z_{k+1}) - CDF_e(z_k), 0).
+ * idx [E][B+1] int32, frac [E][B+1], valid [E][B]. */
+int pfn_ensemble_combine(pfn_ctx* ctx, const float* logits, int64_t ld_logits, int64_t member_stride, int n_members,
+                         int64_t M, const int32_t* idx, const float* frac, const uint8_t* valid, float* out,
+                         int64_t ld_out, void* stream);
 
 #ifdef __cplusplus
 }

@@ -25,6 +25,7 @@
 #endif
 #include "small_kernels.cuh"
 #include "filter_kernels.cuh"
+#include "ensemble_kernels.cuh"
 
 namespace pfn {
 std::string& last_error() {
@@ -777,6 +778,61 @@ int pfn_debug_last_states(pfn_ctx* c, float* out, int64_t max_floats, void* stre
     PFN_REQUIRE(n > 0 && n <= max_floats, "no forward has run or output buffer too small");
     PFN_CUDA_OK(cudaSetDevice(c->device));
     PFN_CUDA_OK(cudaMemcpyAsync(out, c->xf, (size_t)n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int pfn_member_transform(pfn_ctx* c, const pfn_member_desc* d, const float* X, int64_t ldx, int64_t M, float* out,
+                         int64_t ld_out, void* stream) {
+    PFN_REQUIRE(c && d && (M == 0 || (X && out)), "null argument");
+    PFN_REQUIRE(d->kind == 0 || d->kind == 1, "member kind must be 0 (quantile) or 1 (safepower)");
+    PFN_REQUIRE(d->n_features_in >= 1 && d->n_keep >= 1 && d->n_keep <= d->n_features_in && d->keep, "bad kept-feature list");
+    const int n_el = d->kind == 0 ? 2 * d->n_keep : d->n_keep;
+    const int svd_k = d->kind == 0 ? d->svd_k : 0;
+    const int n_base = n_el + svd_k + (d->fingerprint ? 1 : 0);
+    PFN_REQUIRE(n_base <= kMaxBase && d->n_out == n_base && d->perm, "member feature count out of range");
+    PFN_REQUIRE(d->kind == 0 ? (d->n_quantiles >= 2 && d->quantiles) : (d->safepower != nullptr), "missing member tables");
+    PFN_REQUIRE(svd_k == 0 || (d->svd_inv_scale && d->svd_vt), "missing SVD tables");
+    PFN_REQUIRE(ldx >= d->n_features_in && ld_out >= d->n_out, "row stride smaller than feature count");
+    if (M == 0) return 0;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    MemberXformArgs a{};
+    a.X = X; a.ldx = ldx; a.M = M; a.F_in = d->n_features_in; a.out = out; a.ld_out = ld_out;
+    a.n_keep = d->n_keep; a.keep = d->keep; a.kind = d->kind; a.nq = d->n_quantiles; a.quantiles = d->quantiles;
+    a.sp = d->safepower; a.svd_k = svd_k; a.svd_inv_scale = d->svd_inv_scale; a.svd_vt = d->svd_vt;
+    a.fingerprint = d->fingerprint; a.n_out = d->n_out; a.perm = d->perm;
+    TimeScope ts(c, st, KC_OTHER, 0.0);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(M, XF_WARPS), (int64_t)c->num_sms * 8);
+    member_transform_kernel<<<grid, XF_WARPS * 32, 0, st>>>(a);
+    PFN_CUDA_OK(cudaGetLastError());
+    c->launches++;
+    return 0;
+}
+
+int pfn_ensemble_combine(pfn_ctx* c, const float* logits, int64_t ld_logits, int64_t member_stride, int n_members, int64_t M,
+                         const int32_t* idx, const float* frac, const uint8_t* valid, float* out, int64_t ld_out,
+                         void* stream) {
+    PFN_REQUIRE(c && (M == 0 || (logits && out)) && idx && frac && valid, "null argument");
+    PFN_REQUIRE(n_members >= 1, "need at least one member");
+    const int B = c->cfg.num_buckets;
+    PFN_REQUIRE(ld_logits >= B && ld_out >= B, "row stride smaller than the bucket count");
+    if (M == 0) return 0;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = combine_smem_bytes(B);
+    static bool configured_dev[64] = {};
+    if (!configured_dev[c->device & 63]) {
+        PFN_CUDA_OK(cudaFuncSetAttribute(ensemble_combine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured_dev[c->device & 63] = true;
+    }
+    CombineArgs a{};
+    a.logits = logits; a.ld_logits = ld_logits; a.member_stride = member_stride; a.E = n_members; a.B = B; a.M = M;
+    a.idx = idx; a.frac = frac; a.valid = valid; a.out = out; a.ld_out = ld_out;
+    TimeScope ts(c, st, KC_OTHER, 0.0);
+    const unsigned grid = (unsigned)std::min<int64_t>(M, (int64_t)c->num_sms * 2);
+    ensemble_combine_kernel<<<grid, CB_THREADS, smem, st>>>(a);
+    PFN_CUDA_OK(cudaGetLastError());
+    c->launches++;
     return 0;
 }
 

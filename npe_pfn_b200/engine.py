@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "pfn_forward_logits", "pfn_head_sample", "pfn_head_nll", "pfn_sample", "pfn_logprob", "pfn_accept_compact",
     "pfn_filter_context",
     "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_slot_state", "pfn_slot_import",
-    "pfn_debug_last_states",
+    "pfn_debug_last_states", "pfn_member_transform", "pfn_ensemble_combine",
 ]
 
 _LIB = None
@@ -92,6 +92,10 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_slot_import.argtypes = [vp, c.c_int, i64, c.c_int, vp, vp, vp, vp]
     L.pfn_debug_last_states.restype = c.c_int
     L.pfn_debug_last_states.argtypes = [vp, vp, i64, vp]
+    L.pfn_member_transform.restype = c.c_int
+    L.pfn_member_transform.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp]
+    L.pfn_ensemble_combine.restype = c.c_int
+    L.pfn_ensemble_combine.argtypes = [vp, vp, i64, i64, c.c_int, i64, vp, vp, vp, vp, i64, vp]
     _LIB = L
     return L
 

@@ -10,9 +10,10 @@ The reference reaches its arithmetic through (`/root/reference/npe_pfn/npe_pfn.p
 
 `B200TabPFNRegressor` honours exactly that: constructible from kwargs alone, `fit` (re)builds the
 context K/V cache in HBM (`pfn_prefill`), `predict` runs the test rows against it
-(`pfn_forward_logits`), and the criterion maps to `pfn_head_sample` / `pfn_head_nll`.  Single
-estimator, identity preprocessing, softmax temperature 0.9; the 8-member
-sklearn-preprocessing ensemble of upstream `tabpfn` is a "next" row.
+(`pfn_forward_logits`), and the criterion maps to `pfn_head_sample` / `pfn_head_nll`.  Softmax
+temperature 0.9.  `n_estimators=1` (the default here) is a single estimator with
+identity preprocessing; `n_estimators > 1` runs upstream's preprocessing ensemble (SURVEY.md §8f-1,
+`ensemble.py`: per-member feature pipelines, target transforms, re-binning and probability averaging).
 """
 from __future__ import annotations
 
@@ -63,21 +64,38 @@ class B200Criterion:
 class B200TabPFNRegressor:
     def __init__(self, weights: Optional[PFNWeights] = None, device: Optional[int] = None,
                  softmax_temperature: float = 0.9, n_estimators: int = 1, output_device: str = "cpu",
-                 slot: int = 0, engine: Optional[Engine] = None, **_ignored):
-        if n_estimators != 1:
-            raise NotImplementedError("npe_pfn_b200 implements a single estimator with identity preprocessing "
-                                      "(the tabpfn ensemble is listed as a next row in DESIGN.md)")
-        self.engine = engine or get_engine(device=device, weights=weights, softmax_temperature=softmax_temperature)
+                 slot: int = 0, engine: Optional[Engine] = None, random_state: int = 0,
+                 fingerprint_feature: bool = True, svd_features: bool = True, **_ignored):
+        if n_estimators < 1:
+            raise ValueError("n_estimators must be >= 1")
+        self.n_estimators = int(n_estimators)
+        kw = {} if self.n_estimators == 1 else {"max_slots": 16 * self.n_estimators}
+        self.engine = engine or get_engine(device=device, weights=weights, softmax_temperature=softmax_temperature, **kw)
+        self.member_specs = None
+        if self.n_estimators > 1:
+            from .ensemble import make_members
+            self.member_specs = make_members(self.n_estimators, random_state, fingerprint_feature, svd_features)
+            assert self.engine.max_slots >= self.n_estimators, "engine has fewer slots than ensemble members"
         self.slot = slot
         self.output_device = output_device
         self._fitted = False
+        self._ens = None
 
     def fit(self, X: torch.Tensor, y: torch.Tensor):
         X = torch.as_tensor(X, dtype=torch.float32)
         y = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
         assert X.ndim == 2 and X.shape[0] == y.shape[0], "fit expects X[N, F], y[N]"
-        self.engine.__dict__.get("_slot_tags", {}).pop(self.slot, None)  # the slot no longer holds a posterior's cache
-        self.engine.prefill(self.slot, X, y)
+        tags = self.engine.__dict__.get("_slot_tags", {})
+        if self.n_estimators == 1:
+            tags.pop(self.slot, None)  # the slot no longer holds a posterior's cache
+            self.engine.prefill(self.slot, X, y)
+        else:
+            from .ensemble import EnsembleDim
+            slot0 = self.slot * self.n_estimators
+            for e in range(self.n_estimators):
+                tags.pop(slot0 + e, None)
+            dev = self.engine.device
+            self._ens = EnsembleDim(self.engine, self.member_specs, slot0).fit(X.to(dev), y.to(dev))
         self._fitted = True
         return self
 
@@ -87,6 +105,9 @@ class B200TabPFNRegressor:
         if output_type != "full":
             raise NotImplementedError("only output_type='full' is on the NPE-PFN hot path")
         X = torch.as_tensor(X, dtype=torch.float32)
+        if self._ens is not None:
+            logits = self._ens.logits(X.to(self.engine.device))
+            return {"criterion": B200Criterion(self.engine, self._ens.head_slot, self.output_device), "logits": logits}
         logits = self.engine.forward_logits(self.slot, X)
         return {"criterion": B200Criterion(self.engine, self.slot, self.output_device), "logits": logits}
 

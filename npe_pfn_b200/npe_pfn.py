@@ -144,15 +144,62 @@ class NPE_PFN_Core:
         return self._ctx
 
     def _ensure_slot(self, ctx: _Context, d: int) -> int:
-        """Slot holding the K/V cache of (ctx, d); prefilled on first use, shared engine slots are tagged."""
+        """Slot holding the K/V cache of (ctx, d); prefilled on first use, shared engine slots are tagged.
+        With `n_estimators > 1` the dimension owns a block of slots (one per member, `ensemble.EnsembleDim`) and the
+        returned slot is the one whose borders are the common borders (member 0)."""
         eng = self.engine
-        slot = d % eng.max_slots
+        E = self._model.n_estimators
         tag = (self._uid, ctx.key, d)
         tags = eng.__dict__.setdefault("_slot_tags", {})
-        if tags.get(slot) != tag:
-            eng.prefill_joint(slot, ctx.joint, ctx.dim_x + d)
-            tags[slot] = tag
-        return slot
+        if E == 1:
+            slot = d % eng.max_slots
+            if tags.get(slot) != tag:
+                eng.prefill_joint(slot, ctx.joint, ctx.dim_x + d)
+                tags[slot] = tag
+            return slot
+        slot0 = (d % (eng.max_slots // E)) * E
+        dims = eng.__dict__.setdefault("_ensemble_dims", {})
+        if tags.get(slot0) != tag or slot0 not in dims:
+            from .ensemble import EnsembleDim
+            nf = ctx.dim_x + d
+            dims[slot0] = EnsembleDim(eng, self._model.member_specs, slot0).fit(ctx.joint[:, :nf], ctx.joint[:, nf])
+            for e in range(E):
+                tags.pop(slot0 + e, None)
+            tags[slot0] = tag
+        return slot0
+
+    def _ens(self, slot: int):
+        return self.engine.__dict__["_ensemble_dims"][slot] if self._model.n_estimators > 1 else None
+
+    def _logits(self, slot: int, X: Tensor) -> Tensor:
+        """predict(output_type="full")["logits"] for raw test rows (single estimator or member ensemble)."""
+        ens = self._ens(slot)
+        return self.engine.forward_logits(slot, X) if ens is None else ens.logits(X)
+
+    def _sample_step(self, slot: int, buf: Tensor, n_features: int, **kw):
+        """One autoregressive step on the rows of `buf`: draw column `n_features` given columns [:n_features]."""
+        eng = self.engine
+        ens = self._ens(slot)
+        if ens is None:
+            return eng.sample_step(slot, buf, n_features, n_features, **kw)
+        uniforms, bins, lp, row0 = kw.pop("uniforms", None), kw.pop("bins", None), kw.pop("out_logp", None), kw.pop("row0", 0)
+        for r0 in range(0, buf.shape[0], ens.chunk_rows):
+            r1 = min(r0 + ens.chunk_rows, buf.shape[0])
+            logits = ens.logits(buf[r0:r1, :n_features])
+            eng.head_sample(slot, logits, uniforms=None if uniforms is None else uniforms[r0:r1], row0=row0 + r0,
+                            out_theta=buf[r0:r1, n_features], ld_theta=buf.stride(0),
+                            out_logp=None if lp is None else lp[r0:r1], bins=None if bins is None else bins[r0:r1], **kw)
+
+    def _logprob_step(self, slot: int, buf: Tensor, n_features: int, lp: Tensor, eps: float):
+        eng = self.engine
+        ens = self._ens(slot)
+        if ens is None:
+            return eng.logprob_step(slot, buf, n_features, n_features, lp, eps=eps, accumulate=True)
+        for r0 in range(0, buf.shape[0], ens.chunk_rows):
+            r1 = min(r0 + ens.chunk_rows, buf.shape[0])
+            logits = ens.logits(buf[r0:r1, :n_features])
+            eng.head_nll(slot, logits, buf[r0:r1, n_features], eps=eps, ld_y=buf.stride(0), out_logp=lp[r0:r1],
+                         accumulate=True)
 
     def prefill(self, x: Tensor):
         """Build the K/V caches of every dimension for the context of `x` now (otherwise done lazily)."""
@@ -174,6 +221,7 @@ class NPE_PFN_Core:
         ctx = self._prepare_context(x)
         eng = self.engine
         assert ctx.dim_theta <= eng.max_slots, "sharded prefill keeps one slot per dimension"
+        assert self._model.n_estimators == 1, "sharded prefill exchanges single-estimator slots"
         tags = eng.__dict__.setdefault("_slot_tags", {})
         if all(tags.get(d) == (self._uid, ctx.key, d) for d in range(ctx.dim_theta)):
             return self  # every slot is current: nothing to build or exchange
@@ -235,13 +283,13 @@ class NPE_PFN_Core:
             b_d = bins[d] if bins is not None else None
             if d == 0 and repeat_x and M > 1 and xd.shape[0] == 1:
                 # every test row is the same observation: one forward row, M inverse-CDF draws from its logits
-                logits = eng.forward_logits(slot, buf[:1, :dx])
+                logits = self._logits(slot, buf[:1, :dx])
                 eng.head_sample(slot, logits, M=M, uniforms=u_d, seed=seed or 0, row0=row0, offset=d,
                                 out_theta=buf[:, dx], ld_theta=buf.stride(0), out_logp=lp, eps=eps, accumulate=True,
                                 bins=b_d)
             else:
-                eng.sample_step(slot, buf, dx + d, dx + d, uniforms=u_d, seed=seed or 0, row0=row0, offset=d,
-                                out_logp=lp, eps=eps, accumulate=True, bins=b_d)
+                self._sample_step(slot, buf, dx + d, uniforms=u_d, seed=seed or 0, row0=row0, offset=d,
+                                  out_logp=lp, eps=eps, accumulate=True, bins=b_d)
         theta = buf[:, dx:]
         if not return_device:
             theta = theta.cpu()
@@ -272,15 +320,15 @@ class NPE_PFN_Core:
             slot = self._ensure_slot(ctx, d)
             if d == 0 and n > 1:
                 # rows of one observation share their features: num_obs forward rows, n draws from each
-                logits = eng.forward_logits(slot, xd)
+                logits = self._logits(slot, xd)
                 for o in range(num_obs):
                     eng.head_sample(slot, logits[o:o + 1], M=n, seed=seed, row0=row0 + o * n, offset=0,
                                     out_theta=buf[o * n:(o + 1) * n, dx], ld_theta=buf.stride(0),
                                     out_logp=lp[o * n:(o + 1) * n] if lp is not None else None, eps=eps,
                                     accumulate=True)
             else:
-                eng.sample_step(slot, buf, dx + d, dx + d, seed=seed, row0=row0, offset=d, out_logp=lp, eps=eps,
-                                accumulate=True)
+                self._sample_step(slot, buf, dx + d, seed=seed, row0=row0, offset=d, out_logp=lp, eps=eps,
+                                  accumulate=True)
         theta = buf[:, dx:].reshape(num_obs, n, dth)
         if lp is not None:
             lp = lp.reshape(num_obs, n)
@@ -310,10 +358,10 @@ class NPE_PFN_Core:
             slot = self._ensure_slot(ctx, d)
             if d == 0 and repeat_x and m > 1 and xd.shape[0] == 1:
                 # one observation: dimension 0 sees identical features in every row -> one forward row, m targets
-                logits = eng.forward_logits(slot, buf[:1, :dx])
+                logits = self._logits(slot, buf[:1, :dx])
                 eng.head_nll(slot, logits, buf[:, dx], eps=eps, ld_y=buf.stride(0), out_logp=lp, accumulate=True)
             else:
-                eng.logprob_step(slot, buf, dx + d, dx + d, lp, eps=eps, accumulate=True)
+                self._logprob_step(slot, buf, dx + d, lp, eps)
         return lp if return_device else lp.cpu()
 
     # -- public API -----------------------------------------------------------------------------------------

@@ -1,0 +1,160 @@
+"""GPU parity tests (`-m gpu`) of the ensemble path (`n_estimators > 1`): the library's
+`pfn_member_transform` / `pfn_ensemble_combine` kernels and the host fit (npe_pfn_b200/ensemble.py) against the
+sklearn-backed oracle (oracle/ensemble.py) on the same seeded inputs.
+
+Tolerances: the feature pipelines are fp32 on the device against sklearn's fp64 -> 2e-4 absolute on transformed features
+(SVD components 2e-3: the basis comes from an fp32 base matrix); the combination given IDENTICAL member logits -> 2e-4
+on log-probabilities above 1e-12; end to end (bf16 transformer vs fp32 oracle) the same logit bars as the
+single-estimator path (tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_ATOL = 0.25
+LOGIT_MEAN_ATOL = 0.035
+
+
+def _data(n, f, seed, m=64):
+    g = np.random.default_rng(seed)
+    X = g.normal(size=(n + m, f))
+    X[:, 1 % f] = np.exp(X[:, 1 % f])
+    if f > 2:
+        X[:, 2] = np.round(X[:, 2], 1)
+    y = 0.5 * X[:, 0] + 0.3 * g.normal(size=n + m) + (X[:, -1] > 0) * 1.5
+    X = X.astype(np.float32)
+    return torch.from_numpy(X[:n]), torch.from_numpy(y[:n].astype(np.float32)), torch.from_numpy(X[n:])
+
+
+@pytest.fixture(scope="module")
+def ens_engine(weights):
+    from npe_pfn_b200.engine import Engine
+    return Engine(weights=weights, max_slots=16)
+
+
+@pytest.mark.parametrize("N,F,E", [(200, 3, 4), (97, 5, 8), (400, 10, 4), (33, 1, 2)])
+def test_members_and_combined_logits_vs_oracle(ens_engine, weights, N, F, E):
+    from npe_pfn_b200.ensemble import EnsembleDim, make_members
+    from oracle import ensemble as orc
+    Xc, yc, Xt = _data(N, F, seed=N + F)
+    if F >= 5:
+        Xc[:, 4] = 2.5  # constant on the context: removed by every member
+    dev = ens_engine.device
+    ens = EnsembleDim(ens_engine, make_members(E, 3), 0).fit(Xc.to(dev), yc.to(dev))
+    ref = orc.OracleEnsembleRegressor(weights=weights, n_estimators=E, random_state=3).fit(Xc, yc)
+    # 1. per-member feature pipelines of the test rows
+    for m, om in zip(ens.members, ref.members):
+        got = ens._transform(m, Xt.to(dev)).cpu().numpy()
+        want = om.transform_x(Xt.numpy())
+        assert got.shape == want.shape
+        inv = np.argsort(np.random.default_rng(m.spec.perm_seed).permutation(got.shape[1]))
+        g0, w0 = got[:, inv], want[:, inv]  # pre-shuffle column order
+        nk = m.desc.n_keep
+        n_el = 2 * nk if m.spec.x_kind == "quantile" else nk
+        assert np.abs(g0[:, :n_el] - w0[:, :n_el]).max() <= 2e-4, (m.spec, np.abs(g0[:, :n_el] - w0[:, :n_el]).max())
+        if m.spec.x_kind == "quantile" and m.desc.svd_k:
+            k = m.desc.svd_k
+            assert np.abs(g0[:, n_el:n_el + k] - w0[:, n_el:n_el + k]).max() <= 2e-3
+        assert np.array_equal(g0[:, -1], w0[:, -1])  # fingerprint: bit exact
+        if m.lam_y is not None:
+            assert abs(m.lam_y - om.lam_y) <= 5e-4
+    # 2. combination kernel on IDENTICAL member logits
+    ml = ref.member_logits(Xt)
+    B = weights.cfg.num_buckets
+    ld = (B + 3) // 4 * 4
+    buf = torch.zeros(E, Xt.shape[0], ld, dtype=torch.float32, device=dev)
+    for e in range(E):
+        buf[e, :, :B] = torch.from_numpy(ml[e]).to(dev)
+    out = torch.empty(Xt.shape[0], ld, dtype=torch.float32, device=dev)
+    # oracle tables -> device arrays (so that only the kernel arithmetic is compared)
+    idx = torch.full((E, B + 1), -1, dtype=torch.int32)
+    frac = torch.zeros(E, B + 1)
+    valid = torch.ones(E, B, dtype=torch.uint8)
+    for e, tb in enumerate(ref.tables):
+        if tb is not None:
+            idx[e], frac[e], valid[e] = torch.from_numpy(tb[0]), torch.from_numpy(tb[1]), torch.from_numpy(tb[2].astype(np.uint8))
+    from npe_pfn_b200.engine import _ptr
+    idx_d, frac_d, valid_d = idx.to(dev), frac.to(dev), valid.to(dev)  # keep the device copies alive over the launch
+    ens_engine._check(ens_engine.lib.pfn_ensemble_combine(ens_engine._h, _ptr(buf), ld, buf.stride(0), E, Xt.shape[0],
+                                                          _ptr(idx_d), _ptr(frac_d), _ptr(valid_d),
+                                                          _ptr(out), ld, ens_engine._stream()))
+    torch.cuda.synchronize()
+    want = orc.combine(ml, ref.tables)
+    got = out[:, :B].cpu().numpy()
+    big = want > np.log(1e-12)
+    assert np.abs(got[big] - want[big]).max() <= 2e-4
+    assert np.all(got[~big] < np.log(1e-11))
+    # 3. the product's own tables agree with the oracle's (same lambdas up to the optimiser tolerance)
+    for e, tb in enumerate(ref.tables):
+        if tb is None:
+            assert int(ens.idx[e, 0]) < 0
+        else:
+            assert np.mean(ens.idx[e].cpu().numpy() != tb[0]) <= 0.02  # a border can fall either side of a bucket edge
+    # 4. end to end: combined logits (bf16 transformer) vs oracle (fp32)
+    got = ens.logits(Xt.to(dev)).cpu()
+    want_t = ref.predict(Xt)["logits"]
+    fin = torch.isfinite(want_t) & (want_t > -25)
+    d = (got - want_t)[fin].abs()
+    print(f"N={N} F={F} E={E}: max|dlogit|={d.max():.4f} mean={d.mean():.5f}")
+    assert d.max() <= LOGIT_ATOL and d.mean() <= LOGIT_MEAN_ATOL
+
+
+def test_estimator_protocol_with_ensemble(weights):
+    """fit / predict / criterion.sample / criterion(logits, y) with n_estimators = 4 (the reference's five calls)."""
+    from npe_pfn_b200.estimator import B200TabPFNRegressor
+    from oracle.ensemble import OracleEnsembleRegressor
+    Xc, yc, Xt = _data(150, 4, seed=11, m=40)
+    model = B200TabPFNRegressor(weights=weights, n_estimators=4, random_state=1).fit(Xc, yc)
+    pred = model.predict(Xt, output_type="full", quantiles=[])
+    ref = OracleEnsembleRegressor(weights=weights, n_estimators=4, random_state=1).fit(Xc, yc).predict(Xt)
+    u = torch.rand(Xt.shape[0], generator=torch.Generator().manual_seed(0)).clamp(1e-4, 1 - 1e-4)
+    th = pred["criterion"].sample(pred["logits"], uniforms=u)
+    th_ref = ref["criterion"].sample(ref["logits"], uniforms=u)
+    assert th.shape == (40,) and torch.isfinite(th).all()
+    # same uniforms, logits within the bf16 bar -> draws differ by a small fraction of the target's spread
+    assert (th - th_ref).abs().median() <= 0.05 * yc.std()
+    nll = pred["criterion"](pred["logits"], th_ref)
+    nll_ref = ref["criterion"](ref["logits"], th_ref)
+    assert (nll - nll_ref).abs().max() <= 0.1
+
+
+def test_posterior_sample_and_log_prob_with_ensemble(weights):
+    """NPE_PFN_Core with regressor_init_kwargs={'n_estimators': 2}: sample + log_prob run through the ensemble path,
+    chunk invariance, and dimension-0 single-row elimination agrees with the row-by-row path."""
+    from npe_pfn_b200 import NPE_PFN_Core
+    g = torch.Generator().manual_seed(5)
+    theta = torch.randn(120, 2, generator=g)
+    x = theta @ torch.randn(2, 3, generator=g) + 0.1 * torch.randn(120, 3, generator=g)
+    prior = torch.distributions.Independent(torch.distributions.Normal(torch.zeros(2), 3 * torch.ones(2)), 1)
+    post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"weights": weights, "n_estimators": 2})
+    post.append_simulations(theta, x)
+    xo = x[:1]
+    u = torch.rand(50, 2, generator=g).clamp(1e-4, 1 - 1e-4)
+    th, lp = post._sample(50, xo, with_log_prob=True, uniforms=u)
+    assert th.shape == (50, 2) and torch.isfinite(th).all() and torch.isfinite(lp).all()
+    lp2 = post.log_prob(th, xo)
+    assert torch.allclose(lp, lp2, atol=2e-3)
+    # row-by-row (no dimension-0 shortcut: repeat_x=False) gives the same draws for the same uniforms
+    th3, _ = post._sample(50, xo.expand(50, -1), repeat_x=False, uniforms=u)
+    assert (th - th3).abs().max() <= 1e-3 * (1 + th.abs().max())
+    s = post.sample((30,), x=xo)
+    assert s.shape == (30, 2)
+
+
+def test_ensemble_vs_golden(ens_engine, weights):
+    """CUDA ensemble path against the frozen oracle outputs (tests/golden/ensemble_golden.pt)."""
+    import os
+    from npe_pfn_b200.ensemble import EnsembleDim, make_members
+    gold = torch.load(os.path.join(os.path.dirname(__file__), "golden", "ensemble_golden.pt"), weights_only=False)
+    dev = ens_engine.device
+    specs = make_members(4, 0)
+    assert [(s.x_kind, s.y_kind, s.perm_seed) for s in specs] == gold["specs"]
+    ens = EnsembleDim(ens_engine, specs, 4).fit(gold["Xc"].to(dev), gold["yc"].to(dev))
+    for m, feat in zip(ens.members, gold["features"]):
+        got = ens._transform(m, gold["Xt"].to(dev)).cpu()
+        assert (got - feat).abs().max() <= 2e-3
+    lg = ens.logits(gold["Xt"].to(dev)).cpu()
+    d = (lg[:, gold["cols"]] - gold["logits_cols"]).abs()
+    assert d.max() <= LOGIT_ATOL and d.mean() <= LOGIT_MEAN_ATOL
+    assert (torch.logsumexp(lg, -1) - gold["lse"]).abs().max() <= 1e-2

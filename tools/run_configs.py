@@ -117,8 +117,22 @@ def main():
                 "rows_per_s": M5 / dt, "kv_cache_MB_dim1": info["kv_bytes"] / 1e6,
                 "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9})
 
+    # 6. upstream's default 8-member preprocessing ensemble at the gaussian_linear shape (10k simulations):
+    #     fit of all 8 x 10 member contexts, then S draws
+    g = torch.Generator().manual_seed(1)
+    theta = math.sqrt(0.1) * torch.randn(10_000, 10, generator=g)
+    x = theta + math.sqrt(0.1) * torch.randn(10_000, 10, generator=g)
+    prior = torch.distributions.MultivariateNormal(torch.zeros(10), 0.1 * torch.eye(10))
+    post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"n_estimators": 8}).append_simulations(theta, x)
+    _, dt_fit = timed(lambda: post.prefill(x[:1]))
+    S6 = int(10_000 * a.scale)
+    s, dt = timed(lambda: post.sample((S6,), x[:1], max_sampling_batch_size=S6))
+    assert s.shape == (S6, 10) and torch.isfinite(s).all()
+    out.append({"config": "gaussian_linear, n_estimators=8 ensemble", "fit_seconds_all_dims": dt_fit, "samples": S6,
+                "seconds": dt, "samples_per_s": S6 / dt, "gpu_mem_GB": torch.cuda.max_memory_allocated() / 1e9})
+
     for o in out:
-        print(json.dumps(o))
+        print(json.dumps(o), flush=True)
 
 
 if __name__ == "__main__":
