@@ -152,7 +152,7 @@ typedef struct pfn_member_desc {
     int32_t n_keep;             /* non-constant raw features                                                      */
     const int32_t* keep;        /* [n_keep] raw column indices                                                    */
     int32_t kind;               /* 0: quantile-uniform + original columns (+ SVD components); 1: standardise ->   */
-                                /*    Yeo-Johnson -> standardise ("safepower")                                    */
+                                /*    Yeo-Johnson -> standardise ("safepower"); 2: kept columns as they are       */
     int32_t n_quantiles;        /* kind 0                                                                         */
     const float* quantiles;     /* kind 0: [n_keep][n_quantiles] ascending (references are j / (n_quantiles - 1)) */
     const float* safepower;     /* kind 1: [5][n_keep] = in_mean | 1/in_std | lambda | out_mean | 1/out_std       */

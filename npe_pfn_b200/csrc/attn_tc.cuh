@@ -117,6 +117,14 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
           "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+}
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
@@ -191,15 +199,17 @@ constexpr float kExpMagic = 12582912.0f;  // 1.5 * 2^23: adding it leaves round(
 //               n >= -125 (also maps the -inf of masked keys to 2^-125 ~ 0).
 // POLY16 of every 16 pairs take the FMA form, spread evenly, so the MUFU pipe (16 ex2 / clk / SM, the bound of
 // this kernel) and the FMA pipes work side by side.
-// `between(i)` runs after pair i: the caller's hook for work that should be interleaved with the exponentials (the
-// maximum pass over the NEXT piece, the wait for its TMEM load).
-template <int POLY16, int DEG, typename Between>
-__device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t* pk, float sc, float neg_m, float cm,
-                                              float smin, uint64_t& l2, Between between) {
+// NPAIR pairs starting at pair I0 of a 16-pair pattern (the FMA-form pairs are those i with
+// ((I0 + i + 1) * POLY16) / 16 != ((I0 + i) * POLY16) / 16).
+// `between(i)` runs after pair i (hook for work to interleave with the exponentials; tools/softmax_bench.cu).
+struct NoBetween { __device__ __forceinline__ void operator()(int) const {} };
+template <int POLY16, int DEG, int NPAIR, int I0, typename Between = NoBetween>
+__device__ __forceinline__ void softmax_exp(const uint32_t* s, uint32_t* pk, float sc, float neg_m, float cm, float smin,
+                                            uint64_t& l2, Between between = Between()) {
     const uint64_t SC = pk2(sc, sc), NM = pk2(neg_m, neg_m), CM = pk2(cm, cm), NEG1 = pk2(-1.0f, -1.0f);
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        const bool poly = ((i + 1) * POLY16) / 16 != (i * POLY16) / 16;
+    for (int i = 0; i < NPAIR; ++i) {
+        const bool poly = ((I0 + i + 1) * POLY16) / 16 != ((I0 + i) * POLY16) / 16;
         float p0, p1;
         if (!poly) {
             float x0, x1;
@@ -231,10 +241,10 @@ __device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t*
         between(i);
     }
 }
-template <int POLY16, int DEG>
+template <int POLY16, int DEG, typename Between = NoBetween>
 __device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t* pk, float sc, float neg_m, float cm,
-                                              float smin, uint64_t& l2) {
-    softmax_exp32<POLY16, DEG>(s, pk, sc, neg_m, cm, smin, l2, [](int) {});
+                                              float smin, uint64_t& l2, Between between = Between()) {
+    softmax_exp<POLY16, DEG, 16, 0>(s, pk, sc, neg_m, cm, smin, l2, between);
 }
 
 // POLY16 = 0: every exponential on MUFU; k > 0: k of every 16 pairs on the FMA pipes (softmax_exp32)

@@ -784,13 +784,13 @@ int pfn_debug_last_states(pfn_ctx* c, float* out, int64_t max_floats, void* stre
 int pfn_member_transform(pfn_ctx* c, const pfn_member_desc* d, const float* X, int64_t ldx, int64_t M, float* out,
                          int64_t ld_out, void* stream) {
     PFN_REQUIRE(c && d && (M == 0 || (X && out)), "null argument");
-    PFN_REQUIRE(d->kind == 0 || d->kind == 1, "member kind must be 0 (quantile) or 1 (safepower)");
+    PFN_REQUIRE(d->kind >= 0 && d->kind <= 2, "member kind must be 0 (quantile), 1 (safepower) or 2 (none)");
     PFN_REQUIRE(d->n_features_in >= 1 && d->n_keep >= 1 && d->n_keep <= d->n_features_in && d->keep, "bad kept-feature list");
     const int n_el = d->kind == 0 ? 2 * d->n_keep : d->n_keep;
     const int svd_k = d->kind == 0 ? d->svd_k : 0;
     const int n_base = n_el + svd_k + (d->fingerprint ? 1 : 0);
     PFN_REQUIRE(n_base <= kMaxBase && d->n_out == n_base && d->perm, "member feature count out of range");
-    PFN_REQUIRE(d->kind == 0 ? (d->n_quantiles >= 2 && d->quantiles) : (d->safepower != nullptr), "missing member tables");
+    PFN_REQUIRE(d->kind == 0 ? (d->n_quantiles >= 2 && d->quantiles) : (d->kind == 2 || d->safepower != nullptr), "missing member tables");
     PFN_REQUIRE(svd_k == 0 || (d->svd_inv_scale && d->svd_vt), "missing SVD tables");
     PFN_REQUIRE(ldx >= d->n_features_in && ld_out >= d->n_out, "row stride smaller than feature count");
     if (M == 0) return 0;

@@ -21,7 +21,7 @@ struct MemberXformArgs {
     const float* X; int64_t ldx; int64_t M; int F_in;
     float* out; int64_t ld_out;
     int n_keep; const int32_t* keep;      // kept (non-constant) raw columns
-    int kind;                             // 0 = quantile-uniform + original (+ SVD), 1 = safepower
+    int kind;                             // 0 = quantile-uniform + original (+ SVD), 1 = safepower, 2 = kept columns as they are
     int nq; const float* quantiles;       // [n_keep][nq] ascending
     const float* sp;                      // [5][n_keep]: in_mean | in_inv_std | lambda | out_mean | out_inv_std
     int svd_k; const float* svd_inv_scale; const float* svd_vt;  // [2 n_keep], [svd_k][2 n_keep]
@@ -95,6 +95,8 @@ __global__ void __launch_bounds__(XF_WARPS * 32) member_transform_kernel(MemberX
                 const int f = c < nk ? c : c - nk;
                 const float v = x[a.keep[f]];
                 base[c] = c < nk ? quantile_uniform(v, a.quantiles + (size_t)f * a.nq, a.nq) : v;
+            } else if (a.kind == 2) {
+                base[c] = x[a.keep[c]];
             } else {
                 const float z = (x[a.keep[c]] - a.sp[c]) * a.sp[nk + c];
                 base[c] = (yeo_johnson_f(z, a.sp[2 * nk + c]) - a.sp[3 * nk + c]) * a.sp[4 * nk + c];

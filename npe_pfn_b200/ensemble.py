@@ -25,7 +25,7 @@ from .engine import Engine, _ptr
 
 @dataclass
 class MemberSpec:
-    x_kind: str  # "quantile" | "safepower"
+    x_kind: str  # "quantile" | "safepower" | "none"
     y_kind: str  # "none" | "safepower"
     perm_seed: int
     fingerprint: bool = True
@@ -45,6 +45,15 @@ def make_members(n: int, random_state: int = 0, fingerprint: bool = True, svd: b
         out.append(MemberSpec("quantile" if i < half else "safepower", "none" if j % 2 == 0 else "safepower",
                               int(shifts[i]), fingerprint, svd))
     return out
+
+
+def make_classifier_members(n: int, random_state: int = 0, fingerprint: bool = True, svd: bool = True) -> List[MemberSpec]:
+    """Classifier ensemble (upstream default 4 members): quantile pipeline and untouched features alternate, the
+    target is never transformed (class indices are permuted per member instead, see `EnsembleDim.fit`)."""
+    rng = np.random.default_rng(random_state)
+    start = int(rng.integers(0, 1000))
+    shifts = rng.permutation(np.arange(start, start + n))
+    return [MemberSpec("quantile" if i % 2 == 0 else "none", "none", int(shifts[i]), fingerprint, svd) for i in range(n)]
 
 
 class pfn_member_desc(c.Structure):
@@ -179,9 +188,13 @@ class EnsembleDim:
                                                 M, _ptr(out), m.desc.n_out, eng._stream()))
         return out
 
-    def fit(self, X: torch.Tensor, y: torch.Tensor):
-        """X [N, F] fp32 on the engine's device (rows may be strided), y [N] raw targets."""
+    def fit(self, X: torch.Tensor, y: torch.Tensor, n_classes: int = 0, class_seed: int = 0):
+        """X [N, F] fp32 on the engine's device (rows may be strided), y [N] raw targets.  `n_classes > 0`: y holds
+        class indices; member e is fitted on a seeded permutation of them (`self.class_perms[e]`, upstream's class
+        shuffle) and no target transform applies."""
         eng = self.engine
+        self.n_classes = int(n_classes)
+        self.class_perms = []
         dev = eng.device
         N, F = X.shape
         Xd = X.double()
@@ -238,6 +251,9 @@ class EnsembleDim:
                     m._set("svd_inv_scale", (1.0 / scale).float().contiguous())
                     m._set("svd_vt", (vt * sign[:, None]).float().contiguous())
                 n_base = n_el + d.svd_k + int(spec.fingerprint)
+            elif spec.x_kind == "none":
+                d.kind = 2
+                n_base = nk + int(spec.fingerprint)
             else:
                 d.kind = 1
                 mean_in = Xk.mean(dim=0)
@@ -257,7 +273,12 @@ class EnsembleDim:
             m.n_out = n_base
             m._set("perm", torch.from_numpy(perm.astype(np.int32)).to(dev))
             # target
-            if spec.y_kind == "none":
+            if self.n_classes:
+                cp = np.random.default_rng(class_seed + 7919 * (e + 1)).permutation(self.n_classes) if e else np.arange(self.n_classes)
+                cp = torch.from_numpy(cp).to(dev)
+                self.class_perms.append(cp)
+                target = cp[y.long()].float()
+            elif spec.y_kind == "none":
                 target = y.float()
             else:
                 if lam_y_cache is None:
@@ -272,6 +293,16 @@ class EnsembleDim:
             self.members.append(m)
         self.idx, self.frac, self.valid = idx, frac, valid
         return self
+
+    def class_probabilities(self, X: torch.Tensor) -> torch.Tensor:
+        """Classifier ensemble: mean over members of softmax(first n_classes logits), class permutation undone."""
+        eng = self.engine
+        acc = None
+        for e, m in enumerate(self.members):
+            lg = eng.forward_logits(self.slot0 + e, self._transform(m, X))[:, :self.n_classes]
+            p = torch.softmax(lg, dim=-1)[:, self.class_perms[e]]  # column c <- member column perm[c]
+            acc = p if acc is None else acc + p
+        return acc / self.E
 
     def logits(self, X: torch.Tensor) -> torch.Tensor:
         """Combined logits [M, B] (= log of the member-averaged bucket probabilities) for raw test rows X [M, F]."""

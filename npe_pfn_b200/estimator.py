@@ -128,18 +128,27 @@ class B200TabPFNClassifier:
     """`TabPFNClassifier(**kw).fit(X, y in {0..C-1})` / `.predict_proba(X) -> ndarray[m, C]` as the reference's
     density-ratio wrapper uses it (`/root/reference/npe_pfn/npe_pfn.py:610, 661, 697`): the same per-feature
     transformer with the classifier's own weights, class indices fed unscaled to the y-encoder, a 10-way decoder of
-    which the first `n_classes` logits are softmaxed (temperature 0.9).  Single estimator, identity preprocessing."""
+    which the first `n_classes` logits are softmaxed (temperature 0.9).  `n_estimators=1`: single estimator, identity
+    preprocessing; `n_estimators > 1`: member feature pipelines + per-member class permutation, probabilities averaged
+    (`ensemble.py`)."""
 
     def __init__(self, weights: Optional[PFNWeights] = None, device: Optional[int] = None,
-                 softmax_temperature: float = 0.9, n_estimators: int = 1, engine: Optional[Engine] = None, **_ignored):
-        if n_estimators != 1:
-            raise NotImplementedError("npe_pfn_b200 implements a single estimator with identity preprocessing")
+                 softmax_temperature: float = 0.9, n_estimators: int = 1, engine: Optional[Engine] = None,
+                 random_state: int = 0, fingerprint_feature: bool = True, svd_features: bool = True, **_ignored):
+        if n_estimators < 1:
+            raise ValueError("n_estimators must be >= 1")
+        self.n_estimators = int(n_estimators)
         if engine is None:
             engine = get_engine(device=device, weights=weights or default_classifier_weights(),
-                                softmax_temperature=softmax_temperature, max_slots=1)
+                                softmax_temperature=softmax_temperature, max_slots=self.n_estimators)
             engine.set_option("standardize_y", 0)
         self.engine = engine
         self.n_classes = 0
+        self.random_state = random_state
+        self._ens = None
+        if self.n_estimators > 1:
+            from .ensemble import make_classifier_members
+            self.member_specs = make_classifier_members(self.n_estimators, random_state, fingerprint_feature, svd_features)
 
     def fit(self, X, y):
         X = torch.as_tensor(X, dtype=torch.float32)
@@ -147,6 +156,12 @@ class B200TabPFNClassifier:
         assert X.ndim == 2 and X.shape[0] == y.shape[0], "fit expects X[N, F], y[N]"
         self.n_classes = int(y.max().item()) + 1
         assert 2 <= self.n_classes <= self.engine.cfg.num_buckets
+        if self.n_estimators > 1:
+            from .ensemble import EnsembleDim
+            dev = self.engine.device
+            self._ens = EnsembleDim(self.engine, self.member_specs, 0).fit(X.to(dev), y.to(dev), n_classes=self.n_classes,
+                                                                         class_seed=self.random_state)
+            return self
         self.engine.prefill(0, X, y)
         return self
 
@@ -154,5 +169,7 @@ class B200TabPFNClassifier:
         if not self.n_classes:
             raise RuntimeError("predict_proba called before fit")
         X = torch.as_tensor(X, dtype=torch.float32)
+        if self._ens is not None:
+            return self._ens.class_probabilities(X.to(self.engine.device)).cpu().numpy()
         logits = self.engine.forward_logits(0, X)[:, :self.n_classes]
         return torch.softmax(logits, dim=-1).cpu().numpy()

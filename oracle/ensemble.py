@@ -34,7 +34,7 @@ from . import tabpfn_oracle as model
 
 @dataclass
 class MemberSpec:
-    x_kind: str          # "quantile" | "safepower"
+    x_kind: str          # "quantile" | "safepower" | "none"
     y_kind: str          # "none" | "safepower"
     perm_seed: int
     fingerprint: bool = True
@@ -55,6 +55,18 @@ def make_members(n: int, random_state: int = 0, fingerprint: bool = True, svd: b
         out.append(MemberSpec("quantile" if i < half else "safepower", "none" if j % 2 == 0 else "safepower",
                               int(shifts[i]), fingerprint, svd))
     return out
+
+
+def make_classifier_members(n: int, random_state: int = 0, fingerprint: bool = True, svd: bool = True) -> List[MemberSpec]:
+    """Classifier ensemble: quantile pipeline and untouched features alternate; class indices are permuted per member."""
+    rng = np.random.default_rng(random_state)
+    start = int(rng.integers(0, 1000))
+    shifts = rng.permutation(np.arange(start, start + n))
+    return [MemberSpec("quantile" if i % 2 == 0 else "none", "none", int(shifts[i]), fingerprint, svd) for i in range(n)]
+
+
+def class_permutation(e: int, n_classes: int, class_seed: int = 0) -> np.ndarray:
+    return np.random.default_rng(class_seed + 7919 * (e + 1)).permutation(n_classes) if e else np.arange(n_classes)
 
 
 # ---- fingerprint: 64-bit mix of the fp32 bit patterns of a row -> [0, 1) ---------------------------------------
@@ -142,6 +154,8 @@ class OracleMember:
                 sign[sign == 0] = 1.0
                 self.svd_vt = vt * sign[:, None]
                 self.svd_k = k
+        elif self.spec.x_kind == "none":
+            pass
         else:
             self.sc_in = StandardScaler().fit(Xk)
             Z = self.sc_in.transform(Xk)
@@ -155,6 +169,8 @@ class OracleMember:
             base = np.concatenate([self.qt.transform(Xk), Xk], axis=1)
             if self.svd_k:
                 base = np.concatenate([base, (base / self.svd_scale) @ self.svd_vt.T], axis=1)
+        elif self.spec.x_kind == "none":
+            base = Xk
         else:
             base = self.pt.transform(self.sc_in.transform(Xk))
         if self.spec.fingerprint:
@@ -264,3 +280,40 @@ class OracleEnsembleRegressor:
         assert output_type == "full"
         logits = torch.from_numpy(combine(self.member_logits(X), self.tables))
         return {"criterion": OracleCriterion(self.borders_orig), "logits": logits}
+
+
+class OracleEnsembleClassifier:
+    """`fit(X, y in {0..C-1})` / `predict_proba(X)` with `n_estimators` members (mean of member probabilities)."""
+
+    def __init__(self, weights=None, softmax_temperature: float = 0.9, n_estimators: int = 4, random_state: int = 0,
+                 fingerprint: bool = True, svd: bool = True, chunk: int = 2048, **_ignored):
+        if weights is None:
+            from npe_pfn_b200.estimator import default_classifier_weights
+            weights = default_classifier_weights()
+        self.w = weights
+        self.temperature = float(softmax_temperature)
+        self.specs = make_classifier_members(n_estimators, random_state, fingerprint, svd)
+        self.random_state, self.chunk = random_state, chunk
+
+    def fit(self, X, y):
+        X = torch.as_tensor(X, dtype=torch.float32)
+        y = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
+        self.n_classes = int(y.max().item()) + 1
+        self.members, self.caches, self.perms = [], [], []
+        for e, spec in enumerate(self.specs):
+            m = OracleMember(spec).fit_x(X.numpy())
+            cp = class_permutation(e, self.n_classes, self.random_state)
+            yt = torch.from_numpy(cp[y.long().numpy()].astype(np.float32))
+            self.caches.append(model.prefill(self.w, torch.from_numpy(m.transform_x(X.numpy())), yt))
+            self.members.append(m)
+            self.perms.append(cp)
+        return self
+
+    def predict_proba(self, X) -> np.ndarray:
+        X = torch.as_tensor(X, dtype=torch.float32)
+        acc = 0.0
+        for m, cache, cp in zip(self.members, self.caches, self.perms):
+            Xt = torch.from_numpy(m.transform_x(X.numpy()))
+            lg = model.forward_test(self.w, cache, Xt, chunk=self.chunk).float() / np.float32(self.temperature)
+            acc = acc + torch.softmax(lg[:, :self.n_classes], dim=-1).numpy()[:, cp]
+        return acc / len(self.members)

@@ -158,3 +158,21 @@ def test_ensemble_vs_golden(ens_engine, weights):
     d = (lg[:, gold["cols"]] - gold["logits_cols"]).abs()
     assert d.max() <= LOGIT_ATOL and d.mean() <= LOGIT_MEAN_ATOL
     assert (torch.logsumexp(lg, -1) - gold["lse"]).abs().max() <= 1e-2
+
+
+def test_classifier_ensemble_vs_oracle():
+    """TabPFNClassifier(n_estimators=4) as the density-ratio wrapper would construct it with upstream defaults
+    (npe_pfn.py:610): member pipelines + class permutations, probabilities within 0.02 of the oracle ensemble."""
+    from npe_pfn_b200.estimator import B200TabPFNClassifier, default_classifier_weights
+    from oracle.ensemble import OracleEnsembleClassifier
+    g = torch.Generator().manual_seed(3)
+    X = torch.cat([torch.randn(150, 3, generator=g) + 0.8, torch.randn(150, 3, generator=g) - 0.8])
+    X[:, 1] = torch.exp(X[:, 1])
+    y = torch.cat([torch.ones(150), torch.zeros(150)])
+    Xt = torch.randn(64, 3, generator=g)
+    Xt[:, 1] = torch.exp(Xt[:, 1])
+    got = B200TabPFNClassifier(n_estimators=4, random_state=2).fit(X, y).predict_proba(Xt)
+    ref = OracleEnsembleClassifier(weights=default_classifier_weights(), n_estimators=4, random_state=2).fit(X, y).predict_proba(Xt)
+    assert got.shape == (64, 2) and abs(got.sum(1) - 1).max() < 1e-5
+    print("classifier ensemble max |dp| =", abs(got - ref).max())
+    assert abs(got - ref).max() <= 0.02
