@@ -169,7 +169,7 @@ def run_reference_arm(args):
     last["value"] = v
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": v, "unit": "samples/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * 10_000 / v, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": "gaussian_linear: 10-D theta / 10-D x, 10k simulations (bounded CPU sample)",
                    "n_estimators": 1},
