@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(AT_THREADS, 2) attn_mma_kernel(AttnArgs p) {
 #pragma unroll
         for (int c = 0; c < 4; ++c) o[j][c] = 0.f;
     float mrow[2] = {-INFINITY, -INFINITY}, lrow[2] = {0.f, 0.f};
-    const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+    const float sc = 1.0f;  // queries arrive pre-scaled by kItemScaleLog2 (folded into the projection weights)
 
 #pragma unroll
     for (int s = 0; s < AT_STAGES - 1; ++s) {

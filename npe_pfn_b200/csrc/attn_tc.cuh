@@ -34,9 +34,12 @@ static_assert(TC_BN == 64 || TC_BN == 32, "key tile must be 32 or 64");
 constexpr int TC_Q_BYTES = TC_BM * kDh * 2;           // 8 KB: 128 rows x 64 B
 constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 4 KB: 64 keys x 64 B
 constexpr int TC_STAGE_BYTES = 2 * TC_TILE_BYTES;     // K tile + V tile
-// 66 816 B: three CTAs per SM fit in shared memory (200 KB), a fourth does not.  TMEM: each CTA takes 128 columns
+// 72 960 B: three CTAs per SM fit in shared memory (219 KB), a fourth does not.  TMEM: each CTA takes 128 columns
 // (S0/P0 [0,64), S1/P1 [64,128)) plus a separate 32-column allocation for O: 3 x 160 = 480 of the 512 columns.
-constexpr int TC_SMEM_BYTES = 1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + 256;
+// + the "lean" softmax's third K = 16 block of the Q K^T contraction (32-byte-swizzle rows of 16 bf16): a per-row
+// column pair (-m_hi, -m_lo) on the Q side and a constant (1, 1, 0, ...) on the key side, so S arrives as s - m.
+constexpr int TC_QX_BYTES = TC_BM * 32, TC_KX_BYTES = TC_BN * 32;
+constexpr int TC_SMEM_BYTES = 1024 + TC_Q_BYTES + TC_STAGES * TC_STAGE_BYTES + TC_QX_BYTES + TC_KX_BYTES + 256;
 constexpr int TC_TMEM_COLS_S = 2 * TC_BN, TC_TMEM_COLS_O = 32;
 
 struct TcArgs {
@@ -155,6 +158,17 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
     d |= (uint64_t)4 << 61;            // SWIZZLE_64B
     return d;
 }
+// same for a K = 16 block stored as rows of 32 bytes with the 32-byte swizzle (8-row groups 256 B apart)
+__device__ __forceinline__ uint64_t umma_desc_sw32(uint32_t smem_addr) {
+    uint64_t d = (uint64_t)((smem_addr & 0x3FFFFu) >> 4);
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(256 >> 4) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)6 << 61;  // SWIZZLE_32B
+    return d;
+}
+// byte offset of logical 16-byte chunk 0 of row r in such a block (Swizzle<1,4,3>: address bit 4 ^= bit 7)
+__device__ __forceinline__ uint32_t sw32_chunk0(int r) { return (uint32_t)(r * 32 + (((r >> 2) & 1) << 4)); }
 // instruction descriptor kind::f16: D fp32, A/B bf16 (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
@@ -247,16 +261,66 @@ __device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t*
     softmax_exp<POLY16, DEG, 16, 0>(s, pk, sc, neg_m, cm, smin, l2, between);
 }
 
-// POLY16 = 0: every exponential on MUFU; k > 0: k of every 16 pairs on the FMA pipes (softmax_exp32)
+// "Lean" form: the scores arrive as x = s - m already (scale folded into the Q projection, -m contributed by the
+// third K = 16 block of the Q K^T MMA), so a MUFU pair is two ex2 and nothing else, and the tile maximum is replaced by
+// an overflow check: `ovf` ORs every packed bf16 pair; sign or top exponent bit set (mask 0xC000C000) <=> some P >= 2
+// (or an overflowed FMA-form exponent) <=> a score exceeded the reference by >= 1, and the caller redoes the tile on
+// the general path.
 template <int POLY16, int DEG>
+__device__ __forceinline__ void softmax_exp32_lean(const uint32_t (&s)[32], uint32_t* pk, uint64_t& l2, uint32_t& ovf) {
+    const uint64_t CM = pk2(kExpMagic, kExpMagic), NEG1 = pk2(-1.0f, -1.0f);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        const bool poly = ((i + 1) * POLY16) / 16 != (i * POLY16) / 16;
+        float p0, p1;
+        if (!poly) {
+            p0 = fast_exp2(__uint_as_float(s[2 * i]));
+            p1 = fast_exp2(__uint_as_float(s[2 * i + 1]));
+        } else {
+            const uint64_t X2 = pk2(fmaxf(__uint_as_float(s[2 * i]), -125.0f), fmaxf(__uint_as_float(s[2 * i + 1]), -125.0f));
+            const uint64_t t2 = fadd2(X2, CM);            // magic + n, n = round(x)
+            const uint64_t f2 = fadd2(X2, ffma2(t2, NEG1, CM));  // x - n
+            uint64_t q2;
+            if (DEG == 2) {
+                q2 = ffma2(pk2(0.23842893540859222f, 0.23842893540859222f), f2, pk2(0.7034479975700378f, 0.7034479975700378f));
+                q2 = ffma2(q2, f2, pk2(1.0004431009292603f, 1.0004431009292603f));
+            } else {
+                q2 = ffma2(pk2(0.05517163127660751f, 0.05517163127660751f), f2, pk2(0.2426111251115799f, 0.2426111251115799f));
+                q2 = ffma2(q2, f2, pk2(0.6932609677314758f, 0.6932609677314758f));
+                q2 = ffma2(q2, f2, pk2(0.9999280571937561f, 0.9999280571937561f));
+            }
+            float q0, q1, t0, t1;
+            upk2(q2, q0, q1);
+            upk2(t2, t0, t1);
+            p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+            p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+        }
+        l2 = fadd2(l2, pk2(p0, p1));
+        pk[i] = pack_bf16x2(p0, p1);
+        ovf |= pk[i];
+    }
+}
+
+// POLY16 = 0: every exponential on MUFU; k > 0: k of every 16 pairs on the FMA pipes (softmax_exp32).
+// LEAN = 1: attn_tc v5 (see softmax_exp32_lean); the reference maximum m_cur (integer valued, = rounded running maximum
+// + 7) is baked into S two tiles ahead, a tile takes the fast path when the value baked into it equals m_cur, and the
+// general path (explicit maximum pass, as v4) handles the first two tiles of an item, partial tiles, and the two tiles
+// after a reference change.
+template <int POLY16, int DEG, int LEAN>
+#ifdef PFN_ATTN_MAXNREG
+__global__ void __maxnreg__(PFN_ATTN_MAXNREG)
+#else
 __global__ void __launch_bounds__(TC_THREADS, PFN_ATTN_CTAS)
+#endif
 attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmKV, const TcArgs p) {
     extern __shared__ uint8_t tc_smem_raw[];
     const uint32_t raw = smem_u32(tc_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t sQ = base;
     const uint32_t sKV = base + TC_Q_BYTES;
-    const uint32_t bars = sKV + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t sQx = sKV + TC_STAGES * TC_STAGE_BYTES;
+    const uint32_t sKx = sQx + TC_QX_BYTES;
+    const uint32_t bars = sKx + TC_KX_BYTES;
     // barrier slots (8 B each)
     const uint32_t bar_kv_full = bars;                     // [TC_STAGES]  TMA -> MMA
     const uint32_t bar_kv_empty = bars + 8 * TC_STAGES;    // [TC_STAGES]  MMA -> TMA
@@ -287,6 +351,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         mbar_init(bar_pv, 1);
         mbar_init(bar_o, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (LEAN) {
+        uint32_t* ext = reinterpret_cast<uint32_t*>(tc_smem_raw + (sQx - raw));
+        for (int i = threadIdx.x; i < (TC_QX_BYTES + TC_KX_BYTES) / 4; i += TC_THREADS) ext[i] = 0u;
+        __syncthreads();
+        if (threadIdx.x < TC_BN)  // key side: ones in the two columns that carry -m_hi and -m_lo
+            *reinterpret_cast<uint32_t*>(tc_smem_raw + (sKx - raw) + sw32_chunk0(threadIdx.x)) = 0x3F803F80u;
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     if (warp == 5) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot),
@@ -346,6 +418,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
             constexpr uint32_t idesc_qk = umma_idesc_bf16(TC_BM, TC_BN, 0, 0);
             constexpr uint32_t idesc_pv = umma_idesc_bf16(TC_BM, kDh, 0, 1);
             const uint64_t descQ = umma_desc_sw64(sQ);
+            const uint64_t descQx = umma_desc_sw32(sQx), descKx = umma_desc_sw32(sKx);
             uint32_t g0 = 0, qn = 0;  // g0 = global index of this item's first key tile
             for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x, ++qn, g0 += (uint32_t)ntiles) {
                 auto issue_qk = [&](int j) {
@@ -357,6 +430,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
 #pragma unroll
                     for (int kk = 0; kk < 2; ++kk)  // dh = 32 = 2 x K16; 32 bytes per step inside the swizzle atom
                         umma_ss(d, descQ + (uint64_t)(kk * 2), descK + (uint64_t)(kk * 2), idesc_qk, kk > 0);
+                    if (LEAN) umma_ss(d, descQx, descKx, idesc_qk, 1);  // S -= m (per-row reference maximum)
                     tc_commit(bar_s + 8 * (g & 1u));
                     if (j == ntiles - 1) tc_commit(bar_q_empty);
                 };
@@ -383,94 +457,125 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
         // ================= softmax warps: thread = query row = TMEM lane =================
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         const uint32_t orow = tmem_o + ((uint32_t)(warp * 32) << 16);
-        const float sc = 0.17677669529663687f * 1.4426950408889634f;  // 1/sqrt(32) * log2(e)
+        const float sc = 1.0f;  // queries arrive pre-scaled by kItemScaleLog2 (folded into the projection weights)
+        constexpr float kMargin = LEAN ? 7.0f : 0.0f;  // m_cur = rounded maximum + margin; a new reference is taken when a
+                                                       // tile maximum exceeds m_cur + 8 - margin (lazy rescaling, 2^8)
+        uint8_t* qx_row = tc_smem_raw + (sQx - raw) + sw32_chunk0(warp * 32 + lane);
         uint32_t g = 0, qn = 0;
         for (int64_t item = blockIdx.x; item < p.items; item += gridDim.x, ++qn) {
             const int t = (int)(item / per_col), rem = (int)(item % per_col);
             const int qt = rem / p.heads, h = rem % p.heads;
             const int64_t m0 = (int64_t)qt * TC_BM;
-            // m_ref: integer-valued reference maximum (scaled units); cm = magic - m_ref; smin: score clamp of the FMA form
-            float m_ref = -INFINITY, cm = 0.f, smin = 0.f;
+            // m_cur: integer-valued reference of O and l (scaled units).  LEAN: m_q = value last written to this row's Q
+            // extension, mb[b] = value baked into the S tile that buffer b currently holds (0 until the first write).
+            float m_cur = 0.f, m_q = 0.f, mb0 = 0.f, mb1 = 0.f;
             uint64_t l2 = 0;
             for (int j = 0; j < ntiles; ++j, ++g) {
                 const uint32_t b = g & 1u;
                 const uint32_t scol = trow + b * TC_BN;
                 mbar_wait(bar_s + 8 * b, (g >> 1) & 1u);
                 tc_fence_after();
-                // pass 1: the tile's 32-column pieces -> tile maximum (with 64-key tiles the second piece is re-read
-                // later instead of being kept live, so the kernel fits the register budget of 3 CTAs per SM)
                 constexpr bool kTwo = TC_BN == 64;
-                uint32_t sa[32], sb[kTwo ? 32 : 1];
-                tmem_ld32(scol, sa);
-                if constexpr (kTwo) tmem_ld32(scol + 32, sb);
-                tmem_wait_ld();
                 const int nvalid = (int)min((int64_t)TC_BN, p.N - (int64_t)j * TC_BN);
-                if (nvalid < TC_BN) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        if (i >= nvalid) sa[i] = 0xff800000u;  // -inf
-                        if constexpr (kTwo)
-                            if (32 + i >= nvalid) sb[i] = 0xff800000u;
-                    }
-                }
-                float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-                for (int i = 0; i < 16; ++i) {
-                    if constexpr (kTwo) {
-                        mx0 = fmax3(mx0, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
-                        mx1 = fmax3(mx1, __uint_as_float(sb[2 * i]), __uint_as_float(sb[2 * i + 1]));
-                    } else {
-                        if (i & 1) mx1 = fmax3(mx1, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
-                        else mx0 = fmax3(mx0, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
-                    }
-                }
-                const float mt = fmaxf(mx0, mx1) * sc;
-                // lazy rescaling: keep the old reference maximum unless the new one is more than 2^8 larger
-                const bool need = (j == 0) || (mt > m_ref + 8.0f);
-                if (__any_sync(0xffffffffu, need)) {
-                    float corr = 1.0f;
-                    if (need) {
-                        const float m_new = rintf(mt);
-                        if (j > 0) {
-                            corr = fast_exp2(m_ref - m_new);
-                            float l0, l1;
-                            upk2(l2, l0, l1);
-                            l2 = pk2(l0 * corr, l1 * corr);
-                        }
-                        m_ref = m_new;
-                        cm = kExpMagic - m_ref;
-                        smin = (m_ref - 125.0f) * (1.0f / sc);
-                    }
-                    if (j > 0) {
-                        mbar_wait(bar_pv, (g - 1u) & 1u);  // O += P_{j-1} V_{j-1} must have landed
-                        tc_fence_after();
-                        uint32_t ov[32];
-                        tmem_ld32(orow, ov);
-                        tmem_wait_ld();
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
-                        tmem_st32(orow, ov);
-                    }
-                }
-                // pass 2: P = exp2(S * scale - m_ref) as bf16 pairs
+                const float baked = LEAN ? (b ? mb1 : mb0) : 0.f;
                 uint32_t pk[kTwo ? 32 : 16];
-                softmax_exp32<POLY16, DEG>(sa, pk, sc, -m_ref, cm, smin, l2);
-                if constexpr (kTwo) {
-                    tmem_ld32(scol + 32, sa);
+                bool fast = false;
+                if constexpr (LEAN && kTwo) {
+                    fast = __all_sync(0xffffffffu, j > 0 && nvalid == TC_BN && baked == m_cur);
+                    if (fast) {
+                        uint32_t sa[32], ovf = 0;
+                        uint64_t l2n = l2;
+                        tmem_ld32(scol, sa);
+                        tmem_wait_ld();
+                        softmax_exp32_lean<POLY16, DEG>(sa, pk, l2n, ovf);
+                        tmem_ld32(scol + 32, sa);
+                        tmem_wait_ld();
+                        softmax_exp32_lean<POLY16, DEG>(sa, pk + 16, l2n, ovf);
+                        if (__any_sync(0xffffffffu, (ovf & 0xC000C000u) != 0u)) fast = false;  // redo below (S is intact)
+                        else l2 = l2n;
+                    }
+                }
+                if (!fast) {
+                    // general path.  pass 1: the tile's 32-column pieces -> tile maximum (with 64-key tiles the second
+                    // piece is re-read later instead of being kept live: register budget of 3 CTAs per SM)
+                    uint32_t sa[32], sb[kTwo ? 32 : 1];
+                    tmem_ld32(scol, sa);
+                    if constexpr (kTwo) tmem_ld32(scol + 32, sb);
                     tmem_wait_ld();
                     if (nvalid < TC_BN) {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i)
-                            if (32 + i >= nvalid) sa[i] = 0xff800000u;
+                        for (int i = 0; i < 32; ++i) {
+                            if (i >= nvalid) sa[i] = 0xff800000u;  // -inf
+                            if constexpr (kTwo)
+                                if (32 + i >= nvalid) sb[i] = 0xff800000u;
+                        }
                     }
-                    softmax_exp32<POLY16, DEG>(sa, pk + 16, sc, -m_ref, cm, smin, l2);
-                    tmem_st32(scol, reinterpret_cast<uint32_t(&)[32]>(pk));
-                } else {
-                    tmem_st16(scol, pk);
+                    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) {
+                        if constexpr (kTwo) {
+                            mx0 = fmax3(mx0, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
+                            mx1 = fmax3(mx1, __uint_as_float(sb[2 * i]), __uint_as_float(sb[2 * i + 1]));
+                        } else {
+                            if (i & 1) mx1 = fmax3(mx1, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
+                            else mx0 = fmax3(mx0, __uint_as_float(sa[2 * i]), __uint_as_float(sa[2 * i + 1]));
+                        }
+                    }
+                    const float mt = fmaxf(mx0, mx1) * sc + baked;  // tile maximum in absolute (scaled) units
+                    const bool need = (j == 0) || (mt > m_cur + (8.0f - kMargin));
+                    if (__any_sync(0xffffffffu, need)) {
+                        float corr = 1.0f;
+                        if (need) {
+                            const float m_new = rintf(mt) + kMargin;
+                            if (j > 0) {
+                                corr = fast_exp2(m_cur - m_new);
+                                float l0, l1;
+                                upk2(l2, l0, l1);
+                                l2 = pk2(l0 * corr, l1 * corr);
+                            }
+                            m_cur = m_new;
+                        }
+                        if (j > 0) {
+                            mbar_wait(bar_pv, (g - 1u) & 1u);  // O += P_{j-1} V_{j-1} must have landed
+                            tc_fence_after();
+                            uint32_t ov[32];
+                            tmem_ld32(orow, ov);
+                            tmem_wait_ld();
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                            tmem_st32(orow, ov);
+                        }
+                    }
+                    // pass 2: P = exp2(S - (m_cur - baked)) as bf16 pairs
+                    const float delta = m_cur - baked;
+                    const float cm = kExpMagic - delta, smin = (delta - 125.0f) * (1.0f / sc);
+                    softmax_exp32<POLY16, DEG>(sa, pk, sc, -delta, cm, smin, l2);
+                    if constexpr (kTwo) {
+                        tmem_ld32(scol + 32, sa);
+                        tmem_wait_ld();
+                        if (nvalid < TC_BN) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i)
+                                if (32 + i >= nvalid) sa[i] = 0xff800000u;
+                        }
+                        softmax_exp32<POLY16, DEG>(sa, pk + 16, sc, -delta, cm, smin, l2);
+                    }
+                    if (LEAN && m_cur != m_q) {
+                        // publish the new reference for the tiles whose Q K^T has not been issued yet (j + 2 onwards).
+                        // Q K_{j+1}^T may still be reading the old value: wait for its completion barrier first.
+                        if (j + 1 < ntiles) mbar_wait(bar_s + 8 * (b ^ 1u), ((g + 1u) >> 1) & 1u);
+                        const float hi = 256.0f * rintf(m_cur * (1.0f / 256.0f));
+                        *reinterpret_cast<uint32_t*>(qx_row) = pack_bf16x2(-hi, -(m_cur - hi));
+                        m_q = m_cur;
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    }
                 }
+                if constexpr (kTwo) tmem_st32(scol, reinterpret_cast<uint32_t(&)[32]>(pk));
+                else tmem_st16(scol, pk);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(bar_p + 8 * b);
+                if (b) mb1 = m_q; else mb0 = m_q;  // buffer b next holds tile j + 2, issued after this arrival
             }
             // ---- epilogue: O / l -> bf16 -> global ----
             mbar_wait(bar_o, qn & 1u);
@@ -537,7 +642,7 @@ static inline bool make_map3(CUtensorMap* m, const void* base, uint64_t d0, uint
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int POLY16, int DEG>
+template <int POLY16, int DEG, int LEAN>
 static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUtensorMap& mkv, const TcArgs& p, dim3 grid,
                                               cudaStream_t st) {
     static bool configured_dev[64] = {};  // the attribute is per device
@@ -545,12 +650,12 @@ static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUten
     cudaGetDevice(&dev);
     bool& configured = configured_dev[dev & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<POLY16, DEG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(attn_tc_kernel<POLY16, DEG, LEAN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              TC_SMEM_BYTES);
         if (e != cudaSuccess) return e;
         configured = true;
     }
-    attn_tc_kernel<POLY16, DEG><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
+    attn_tc_kernel<POLY16, DEG, LEAN><<<grid, TC_THREADS, TC_SMEM_BYTES, st>>>(mq, mkv, p);
     return cudaGetLastError();
 }
 
@@ -585,13 +690,14 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, in
     p.num_sms = (uint32_t)num_sms;
     // persist: 3 CTAs per SM walk the items; otherwise one CTA per item (the hardware scheduler staggers them)
     dim3 grid((unsigned)(persist ? std::min<int64_t>(p.items, 3 * (int64_t)num_sms) : p.items));
-    // poly_mod = k + 100 * (degree == 2): k of every 16 exponential pairs on the FMA pipes
-#define PFN_ATTN_CASE(K)                                                      \
-    case K: return launch_attn_tc_impl<K, 3>(mq, mkv, p, grid, st);           \
-    case 100 + K: return launch_attn_tc_impl<K, 2>(mq, mkv, p, grid, st);
+    // poly_mod = k + 100 * (degree == 2) + 1000 * lean: k of every 16 exponential pairs on the FMA pipes
+#define PFN_ATTN_CASE(K)                                                            \
+    case K: return launch_attn_tc_impl<K, 3, 0>(mq, mkv, p, grid, st);              \
+    case 1000 + K: return launch_attn_tc_impl<K, 3, 1>(mq, mkv, p, grid, st);
     switch (poly_mod) {
-        case 0: return launch_attn_tc_impl<0, 3>(mq, mkv, p, grid, st);
-        PFN_ATTN_CASE(4) PFN_ATTN_CASE(5) PFN_ATTN_CASE(6) PFN_ATTN_CASE(7) PFN_ATTN_CASE(8) PFN_ATTN_CASE(10)
+        PFN_ATTN_CASE(0) PFN_ATTN_CASE(3) PFN_ATTN_CASE(4) PFN_ATTN_CASE(5) PFN_ATTN_CASE(6) PFN_ATTN_CASE(7) PFN_ATTN_CASE(8)
+        case 106: return launch_attn_tc_impl<6, 2, 0>(mq, mkv, p, grid, st);
+        case 1106: return launch_attn_tc_impl<6, 2, 1>(mq, mkv, p, grid, st);
         default: return cudaErrorInvalidValue;
     }
 #undef PFN_ATTN_CASE

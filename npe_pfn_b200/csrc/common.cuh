@@ -14,6 +14,10 @@ constexpr int kHeads = 6;      // attention heads
 constexpr int kDh = 32;        // head dim
 constexpr int kHid = 768;      // MLP hidden
 constexpr int kKvRow = 64;     // bf16 per cached key row: K[0..31] | V[32..63]
+// softmax scale of the item attention in base-2 units, 1/sqrt(32) * log2(e).  It is folded into the Q rows of the
+// item-attention projection weights when the bf16 copy of the blob is made (engine.cu), so the item-attention kernels
+// see scores that are already scaled: S = (sc Q) K^T.
+constexpr float kItemScaleLog2 = 0.17677669529663687f * 1.4426950408889634f;
 
 typedef __nv_bfloat16 bf16;
 

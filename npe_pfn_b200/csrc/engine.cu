@@ -91,6 +91,7 @@ struct pfn_ctx {
     int attn_wait_ticks = 1000;
     int attn_stagger_ns = 0;
     int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
+    int attn_lean = 1;  // 1: reference maximum folded into the QK^T MMA, overflow check instead of the maximum pass (attn_tc v5)
     int attn_poly = 5;  // k of every 16 pairs of exponentials on the FMA pipes (+100: degree-2 polynomial); 0 = all on MUFU. r1 sweep: 0 -> 437, 5 -> 473 TFLOP/s
     int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
@@ -195,7 +196,7 @@ int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
     TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
 #ifdef PFN_WITH_ATTN_TC
     if (c->attn_impl == 1) {
-        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly, c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns, st));
+        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly + 1000 * (c->attn_lean && !c->attn_persist), c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns, st));
     } else
 #endif
     {
@@ -397,6 +398,7 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
     }
     if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
     if (const char* e = getenv("NPE_PFN_B200_GEMM")) c->gemm_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
+    if (const char* e = getenv("NPE_PFN_B200_ATTN_LEAN")) c->attn_lean = atoi(e);
     if (const char* e = getenv("NPE_PFN_B200_ATTN_POLY")) {  // tuning / parity sweeps of the exponential split
         if (int rc = pfn_set_option(c, "attn_poly", atoll(e))) { delete c; return rc; }
     }
@@ -404,6 +406,9 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
     PFN_CUDA_OK(cudaMalloc(&c->wb, n_floats * 2));
     PFN_CUDA_OK(cudaMemcpyAsync(c->wf, weights, n_floats * 4, cudaMemcpyDeviceToDevice, st));
     f32_to_bf16_kernel<<<(unsigned)ceil_div((int64_t)n_floats, 256), 256, 0, st>>>(c->wf, c->wb, (int64_t)n_floats);
+    // fold the softmax scale into the item-attention query projection (bf16 copy only; see common.cuh)
+    scale_item_q_kernel<<<(unsigned)ceil_div((int64_t)kE * kE * cfg->nlayers, 256), 256, 0, st>>>(
+        c->wf, c->wb, (int64_t)c->off.item_wqkv, cfg->nlayers, kItemScaleLog2);
     PFN_LAUNCH_OK(c);
     c->slots.resize(cfg->max_slots);
     for (auto& s : c->slots) {
@@ -444,10 +449,11 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_persist")) { c->attn_persist = (int)value; return 0; }
     if (!strcmp(key, "attn_wait_ticks")) { c->attn_wait_ticks = (int)value; return 0; }
     if (!strcmp(key, "attn_stagger_ns")) { c->attn_stagger_ns = (int)value; return 0; }
+    if (!strcmp(key, "attn_lean")) { c->attn_lean = (int)value; return 0; }
     if (!strcmp(key, "attn_poly")) {
         const int64_t k = value % 100;
-        PFN_REQUIRE(value >= 0 && value < 200 && (value == 0 || k == 4 || k == 5 || k == 6 || k == 7 || k == 8 || k == 10),
-                    "attn_poly must be 0 or k (+100 for the degree-2 polynomial), k in 4,5,6,7,8,10");
+        PFN_REQUIRE(value == 106 || (value >= 0 && value < 100 && (k == 0 || (k >= 3 && k <= 8))),
+                    "attn_poly must be 0 or k in 3..8 (106: k = 6 with the degree-2 polynomial)");
         c->attn_poly = (int)value;
         return 0;
     }

@@ -326,6 +326,15 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ in, bf16* __restric
     if (i < n) out[i] = __float2bfloat16_rn(in[i]);
 }
 
+// bf16 copy of the Q rows (first E output features) of every layer's item-attention projection, scaled by `scale`
+__global__ void scale_item_q_kernel(const float* __restrict__ wf, bf16* __restrict__ wb, int64_t off, int L, float scale) {
+    const int64_t per = (int64_t)kE * kE;
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= per * L) return;
+    const int64_t e = off + (i / per) * 3 * per + (i % per);
+    wb[e] = __float2bfloat16_rn(wf[e] * scale);
+}
+
 // ---------------------------------------------------------------------------------------------
 // bar-distribution head (oracle/bar_head.c is the arithmetic spec)
 // ---------------------------------------------------------------------------------------------
