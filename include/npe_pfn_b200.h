@@ -65,7 +65,8 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
 int pfn_ctx_destroy(pfn_ctx* ctx);
 /* runtime switches (no reference counterpart): "attn_impl" / "gemm_impl" 0 = warp-level mma.sync kernels,
  * 1 = tcgen05/TMEM/TMA kernels (default); "chunk_rows" = test rows per pass; "standardize_y" 0 = targets enter the y-encoder unscaled (classifier head:
- * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes (+100: degree-2 polynomial); "time_kernels" 1 = record a
+ * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes; "attn_lean" 1 (default) = reference maximum folded
+ * into the Q K^T MMA + overflow check instead of the maximum pass, 0 = explicit maximum pass per tile; "time_kernels" 1 = record a
  * CUDA event pair around every attention / GEMM launch on its stream (read back with pfn_kernel_times). */
 int pfn_set_option(pfn_ctx* ctx, const char* key, int64_t value);
 
@@ -140,6 +141,10 @@ int pfn_slot_export(pfn_ctx* ctx, int slot, float* stats, float* y_stats, float*
 int pfn_slot_state(pfn_ctx* ctx, int slot, float* enc_state, void* stream);
 int pfn_slot_import(pfn_ctx* ctx, int slot, int64_t N, int F, const float* enc_state, const float* borders,
                     const void* kv, void* stream);
+/* debug: event counters of the tcgen05 item-attention kernel since option "attn_debug" was last set to 1 (host array
+ * of 3): fast-path tiles redone after the overflow check fired, reference-maximum changes after a row's first tile,
+ * tiles (per warp) that took the general path.  Synchronises the device. */
+int pfn_attn_debug_counts(pfn_ctx* ctx, uint64_t* out3);
 /* debug / parity: final-layer states of the last forward chunk [rows, T, E] fp32 */
 int pfn_debug_last_states(pfn_ctx* ctx, float* out, int64_t max_floats, void* stream);
 

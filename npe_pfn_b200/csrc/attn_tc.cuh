@@ -53,6 +53,8 @@ struct TcArgs {
     uint32_t wait_ticks;     // suspend-time hint of the producer / MMA threads' barrier waits (0 = none)
     uint32_t stagger_ns;     // persistent mode: residency slot k (blockIdx / #SMs) starts k * stagger_ns later
     uint32_t num_sms;
+    unsigned long long* dbg;  // optional event counters: [0] fast-path tiles redone after the overflow check fired,
+                              // [1] reference-maximum changes after the first tile, [2] tiles on the general path
 };
 
 // ---- PTX wrappers ------------------------------------------------------------------------------------------
@@ -491,11 +493,16 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         tmem_ld32(scol + 32, sa);
                         tmem_wait_ld();
                         softmax_exp32_lean<POLY16, DEG>(sa, pk + 16, l2n, ovf);
-                        if (__any_sync(0xffffffffu, (ovf & 0xC000C000u) != 0u)) fast = false;  // redo below (S is intact)
-                        else l2 = l2n;
+                        if (__any_sync(0xffffffffu, (ovf & 0xC000C000u) != 0u)) {
+                            fast = false;  // redo below (S is intact)
+                            if (p.dbg && lane == 0) atomicAdd(p.dbg + 0, 1ull);
+                        } else {
+                            l2 = l2n;
+                        }
                     }
                 }
                 if (!fast) {
+                    if (p.dbg && lane == 0) atomicAdd(p.dbg + 2, 1ull);
                     // general path.  pass 1: the tile's 32-column pieces -> tile maximum (with 64-key tiles the second
                     // piece is re-read later instead of being kept live: register budget of 3 CTAs per SM)
                     uint32_t sa[32], sb[kTwo ? 32 : 1];
@@ -528,6 +535,7 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         if (need) {
                             const float m_new = rintf(mt) + kMargin;
                             if (j > 0) {
+                                if (p.dbg) atomicAdd(p.dbg + 1, 1ull);
                                 corr = fast_exp2(m_cur - m_new);
                                 float l0, l1;
                                 upk2(l2, l0, l1);
@@ -660,7 +668,7 @@ static inline cudaError_t launch_attn_tc_impl(const CUtensorMap& mq, const CUten
 }
 
 static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, int poly_mod, int num_sms, int persist,
-                                         uint32_t wait_ticks, uint32_t stagger_ns, cudaStream_t st) {
+                                         uint32_t wait_ticks, uint32_t stagger_ns, unsigned long long* dbg, cudaStream_t st) {
     CUtensorMap mq, mkv;
     TcArgs p{};
     p.O = a.O; p.o_row = a.o_row; p.o_tok = a.o_tok; p.R = a.R; p.N = a.N;
@@ -688,6 +696,7 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, in
     p.wait_ticks = wait_ticks;
     p.stagger_ns = persist ? stagger_ns : 0;
     p.num_sms = (uint32_t)num_sms;
+    p.dbg = dbg;
     // persist: 3 CTAs per SM walk the items; otherwise one CTA per item (the hardware scheduler staggers them)
     dim3 grid((unsigned)(persist ? std::min<int64_t>(p.items, 3 * (int64_t)num_sms) : p.items));
     // poly_mod = k + 100 * (degree == 2) + 1000 * lean: k of every 16 exponential pairs on the FMA pipes

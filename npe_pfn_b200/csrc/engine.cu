@@ -91,6 +91,8 @@ struct pfn_ctx {
     int attn_wait_ticks = 1000;
     int attn_stagger_ns = 0;
     int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
+    int attn_debug = 0;                      // count reference-change events of the item-attention kernel
+    unsigned long long* attn_dbg = nullptr;  // [3] device counters (attn_tc.cuh::TcArgs::dbg)
     int attn_lean = 1;  // 1: reference maximum folded into the QK^T MMA, overflow check instead of the maximum pass (attn_tc v5)
     int attn_poly = 5;  // k of every 16 pairs of exponentials on the FMA pipes (+100: degree-2 polynomial); 0 = all on MUFU. r1 sweep: 0 -> 437, 5 -> 473 TFLOP/s
     int num_sms = 148;
@@ -196,7 +198,8 @@ int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
     TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
 #ifdef PFN_WITH_ATTN_TC
     if (c->attn_impl == 1) {
-        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly + 1000 * (c->attn_lean && !c->attn_persist), c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns, st));
+        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly + 1000 * (c->attn_lean && !c->attn_persist), c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns,
+                                       c->attn_debug ? c->attn_dbg : nullptr, st));
     } else
 #endif
     {
@@ -437,6 +440,7 @@ int pfn_ctx_destroy(pfn_ctx* c) {
     cudaFree(c->cp_counts);
     cudaFree(c->cp_offsets);
     cudaFree(c->flt_ws);
+    cudaFree(c->attn_dbg);
     delete c;
     return 0;
 }
@@ -450,6 +454,12 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_wait_ticks")) { c->attn_wait_ticks = (int)value; return 0; }
     if (!strcmp(key, "attn_stagger_ns")) { c->attn_stagger_ns = (int)value; return 0; }
     if (!strcmp(key, "attn_lean")) { c->attn_lean = (int)value; return 0; }
+    if (!strcmp(key, "attn_debug")) {
+        if (value && !c->attn_dbg) PFN_CUDA_OK(cudaMalloc(&c->attn_dbg, 3 * sizeof(unsigned long long)));
+        if (value) PFN_CUDA_OK(cudaMemset(c->attn_dbg, 0, 3 * sizeof(unsigned long long)));
+        c->attn_debug = (int)value;
+        return 0;
+    }
     if (!strcmp(key, "attn_poly")) {
         const int64_t k = value % 100;
         PFN_REQUIRE(value == 106 || (value >= 0 && value < 100 && (k == 0 || (k >= 3 && k <= 8))),
@@ -784,6 +794,15 @@ int pfn_debug_last_states(pfn_ctx* c, float* out, int64_t max_floats, void* stre
     PFN_REQUIRE(n > 0 && n <= max_floats, "no forward has run or output buffer too small");
     PFN_CUDA_OK(cudaSetDevice(c->device));
     PFN_CUDA_OK(cudaMemcpyAsync(out, c->xf, (size_t)n * 4, cudaMemcpyDeviceToDevice, (cudaStream_t)stream));
+    return 0;
+}
+
+int pfn_attn_debug_counts(pfn_ctx* c, uint64_t* out3) {
+    PFN_REQUIRE(c && out3, "null argument");
+    PFN_REQUIRE(c->attn_dbg, "set option attn_debug first");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    PFN_CUDA_OK(cudaDeviceSynchronize());
+    PFN_CUDA_OK(cudaMemcpy(out3, c->attn_dbg, 3 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -32,7 +32,7 @@ ABI_SYMBOLS = [
     "pfn_forward_logits", "pfn_head_sample", "pfn_head_nll", "pfn_sample", "pfn_logprob", "pfn_accept_compact",
     "pfn_filter_context",
     "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_slot_state", "pfn_slot_import",
-    "pfn_debug_last_states", "pfn_member_transform", "pfn_ensemble_combine",
+    "pfn_debug_last_states", "pfn_member_transform", "pfn_ensemble_combine", "pfn_attn_debug_counts",
 ]
 
 _LIB = None
@@ -92,6 +92,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_slot_import.argtypes = [vp, c.c_int, i64, c.c_int, vp, vp, vp, vp]
     L.pfn_debug_last_states.restype = c.c_int
     L.pfn_debug_last_states.argtypes = [vp, vp, i64, vp]
+    L.pfn_attn_debug_counts.restype = c.c_int
+    L.pfn_attn_debug_counts.argtypes = [vp, c.POINTER(u64)]
     L.pfn_member_transform.restype = c.c_int
     L.pfn_member_transform.argtypes = [vp, vp, vp, i64, i64, vp, i64, vp]
     L.pfn_ensemble_combine.restype = c.c_int
@@ -266,6 +268,12 @@ class Engine:
                                                 _ptr(lo), _ptr(hi), _ptr(mask), _ptr(idx), _ptr(rows), _ptr(count),
                                                 self._stream()))
         return idx, rows, count
+
+    def attn_debug_counts(self):
+        """(redone fast-path tiles, reference changes, general-path tiles) since set_option("attn_debug", 1)."""
+        out = (c.c_uint64 * 3)()
+        self._check(self.lib.pfn_attn_debug_counts(self._h, out))
+        return tuple(int(v) for v in out)
 
     def kernel_times(self, reset: bool = True):
         """{class: (ms, launches, flops)} of the launches recorded while option "time_kernels" was on."""

@@ -556,3 +556,57 @@ def test_tsnpe_rounds_autoregressive(engine):
     assert post._theta_train.shape == (120, 2)
     s = post.sample((50,), torch.zeros(1, 2))
     assert s.shape == (50, 2) and bool(prior.support.check(s).all())
+
+
+@pytest.mark.parametrize("gain", [2.5, 6.0, 25.0])
+def test_item_attention_sharp_scores(weights, gain):
+    """Item attention with LARGE, sharply peaked scores (Q/K projections scaled up): the running maximum of a row keeps
+    growing by more than 2^8 along the keys, so the tcgen05 kernel's reference-change machinery runs for real -- v5's
+    overflow check + redo, the stale tiles after a change, v4's lazy rescaling -- and must agree with the warp-level
+    mma.sync kernel (exact running maximum per tile) and with the fp32 oracle."""
+    from npe_pfn_b200.engine import Engine
+    from npe_pfn_b200.weights import PFNWeights
+    from oracle.estimator import OracleTabPFNRegressor
+    t = {k: v.clone() for k, v in weights.t.items()}
+    t["item_wqkv"][:, :2 * weights.cfg.emsize] *= gain  # Q and K rows: scores grow by gain^2
+    w = PFNWeights(weights.cfg, t)
+    eng = Engine(weights=w, max_slots=2)
+    g = torch.Generator().manual_seed(int(gain))
+    N, F, M = 1300, 3, 300
+    Xc = torch.randn(N, F, generator=g)
+    Xc = Xc[torch.argsort(Xc[:, 0])]  # ordered context: scores trend along the key index
+    yc = Xc[:, 0] + 0.1 * torch.randn(N, generator=g)
+    Xt = torch.randn(M, F, generator=g)
+    outs = {}
+    for name, opts in {"mma": {"attn_impl": 0}, "v4": {"attn_impl": 1, "attn_lean": 0}, "v5": {"attn_impl": 1, "attn_lean": 1},
+                       "v5_mufu": {"attn_impl": 1, "attn_lean": 1, "attn_poly": 0}}.items():
+        eng.set_option("attn_poly", 5)
+        for k, v in opts.items():
+            eng.set_option(k, v)
+        eng.set_option("attn_debug", 1)  # zeroes the event counters
+        eng.prefill(0, Xc, yc)
+        outs[name] = eng.forward_logits(0, Xt).cpu()
+        assert torch.isfinite(outs[name]).all(), name
+        if name.startswith("v"):
+            redo, changes, general = eng.attn_debug_counts()
+            print(f"gain {gain} {name}: redone tiles {redo}, reference changes {changes}, general-path tiles {general}")
+            assert changes > 0, "the test must exercise reference-maximum changes"
+            if name.startswith("v5"):
+                assert redo > 0, "the test must exercise the overflow check + redo path"
+    ref = OracleTabPFNRegressor(weights=w).fit(Xc, yc).predict(Xt)["logits"]
+    for name, o in outs.items():
+        d = (o - ref).abs()
+        print(f"gain {gain} {name}: max|dlogit|={d.max():.4f} mean={d.mean():.5f}")
+    # the three tensor-core variants see the same bf16 operands: they agree with each other at least as well as the
+    # mma.sync kernel agrees with the oracle
+    base = (outs["mma"] - ref).abs()
+    for name in ("v4", "v5", "v5_mufu"):
+        d = (outs[name] - ref).abs()
+        assert d.max() <= max(2.0 * base.max(), LOGIT_ATOL) and d.mean() <= max(1.5 * base.mean(), LOGIT_MEAN_ATOL), name
+    # direct comparison on identical bf16 operands: v5 is as close to the mma.sync kernel as v4 is (differences come from
+    # P rounding / summation order / the FMA-pipe polynomial, amplified by 12 layers of sharp attention)
+    d4 = (outs["v4"] - outs["mma"]).abs()
+    d5 = (outs["v5"] - outs["mma"]).abs()
+    print(f"gain {gain}: v4 vs mma max {d4.max():.4f} mean {d4.mean():.5f} | v5 vs mma max {d5.max():.4f} mean {d5.mean():.5f}")
+    assert d5.mean() <= 1.5 * d4.mean() + 0.01
+    eng.close()

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(128) bench_pipe(float* out, int tiles, float s
 // "lean" variant: what the inner loop would cost if the tensor core delivered x = S*sc - m directly (scale folded
 // into the Q projection, -m as an extra K = 16 block of the QK^T MMA) and the tile maximum were replaced by an
 // overflow check on the packed outputs (OR of all words, one LOP3 per pair).
-template <int K, int DEG>
+template <int K, int DEG, int TRUNC>
 __global__ void __launch_bounds__(128) bench_lean(float* out, int tiles, float sc0) {
     __shared__ uint4 sink[128 * 2];
     uint32_t s[64];
@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(128) bench_lean(float* out, int tiles, float s
                 p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
             }
             l2 = fadd2(l2, pk2(p0, p1));
-            pk[i] = pack_bf16x2(p0, p1);
+            if (TRUNC) asm("prmt.b32 %0, %1, %2, 0x7632;" : "=r"(pk[i]) : "r"(__float_as_uint(p0)), "r"(__float_as_uint(p1)));  // truncating pack
+            else pk[i] = pack_bf16x2(p0, p1);
             ovf |= pk[i];
         }
         volatile uint4* dst = sink + threadIdx.x;
@@ -149,7 +150,8 @@ void run(int ctas_per_sm) {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     auto launch = [&](int n) {
-        if (PIPE == 2) bench_lean<K, DEG><<<148 * ctas_per_sm, 128>>>(out, n, 0.255f);
+        if (PIPE == 3) bench_lean<K, DEG, 1><<<148 * ctas_per_sm, 128>>>(out, n, 0.255f);
+        else if (PIPE == 2) bench_lean<K, DEG, 0><<<148 * ctas_per_sm, 128>>>(out, n, 0.255f);
         else if (PIPE == 1) bench_pipe<K, DEG><<<148 * ctas_per_sm, 128>>>(out, n, 0.255f);
         else bench<K, DEG><<<148 * ctas_per_sm, 128>>>(out, n, 0.255f);
     };
@@ -163,11 +165,14 @@ void run(int ctas_per_sm) {
     int clk; cudaDeviceGetAttribute(&clk, cudaDevAttrClockRate, 0);
     const double per_clk_sm = elems / (ms * 1e-3) / (clk * 1e3) / 148.0;
     printf("%s K=%2d deg=%d warps/SMSP=%d  %7.3f ms  %6.2f elems/clk/SM  = %5.2f clk per warp-elem per SMSP  => %6.1f TFLOP/s equivalent (128 FLOP/elem)\n",
-           PIPE == 2 ? "lean     " : PIPE ? "pipelined" : "two-pass ", K, DEG, ctas_per_sm, ms, per_clk_sm, 128.0 / per_clk_sm, elems / (ms * 1e-3) * 128 / 1e12);
+           PIPE == 3 ? "lean+prmt" : PIPE == 2 ? "lean     " : PIPE ? "pipelined" : "two-pass ", K, DEG, ctas_per_sm, ms, per_clk_sm, 128.0 / per_clk_sm, elems / (ms * 1e-3) * 128 / 1e12);
     cudaFree(out);
 }
 int main(int argc, char** argv) {
     if (argc > 1) {  // lean-variant sweep only
+        for (int w : {3}) {
+            run<0, 3, 3>(w); run<3, 3, 3>(w); run<4, 3, 3>(w); run<5, 3, 3>(w); run<6, 3, 3>(w);
+        }
         for (int w : {1, 3, 4}) {
             run<0, 3>(w); run<0, 3, 2>(w); run<2, 3, 2>(w); run<3, 3, 2>(w); run<4, 3, 2>(w); run<5, 3, 2>(w); run<6, 3, 2>(w); run<8, 3, 2>(w);
         }
