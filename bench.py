@@ -191,6 +191,8 @@ def main():
     ap.add_argument("--gemm", default=None, choices=[None, "mma", "tc"])
     ap.add_argument("--attn-poly", type=int, default=None)
     ap.add_argument("--opt", action="append", default=[], help="engine option key=value (tuning sweeps)")
+    ap.add_argument("--item-gain", type=float, default=1.0,
+                    help="tuning only: scale the item-attention Q/K projection weights (sharper attention scores)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -214,7 +216,10 @@ def main():
     S = args.samples
     theta, x, x_o, prior = make_workload()
     theta_p, x_p, xo_p = theta.pin_memory(), x.pin_memory(), x_o.pin_memory()
-    eng = Engine(weights=PFNWeights.random_init(), device=local_rank, max_slots=16)
+    w_bench = PFNWeights.random_init()
+    if args.item_gain != 1.0:  # not the bench configuration: scores grow by gain^2 (reference-maximum changes per row)
+        w_bench.t["item_wqkv"][:, :2 * w_bench.cfg.emsize] *= args.item_gain
+    eng = Engine(weights=w_bench, device=local_rank, max_slots=16)
     if args.attn:
         eng.set_option("attn_impl", 1 if args.attn == "tc" else 0)
     if args.gemm:
@@ -324,8 +329,8 @@ def main():
     tot_ms = sum(v[0] for v in kt.values())
     roofline = {"bound": "tensor", "kernel": "item attention of test rows vs cached K/V", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # DRAM bytes per launch from ncu (profiles/r1_launch_summary_final.csv: 149 attn_tc launches read
-                # 11 659 MB and wrote 1 931 MB); algorithmic bytes of the largest launch (Q in, O out, K/V) are 152 MB
+                # DRAM bytes per launch from ncu (profiles/r1_launch_summary_v4.csv: 149 attn_tc launches read
+                # 11 658 MB and wrote 1 903 MB); algorithmic bytes of the largest launch (Q in, O out, K/V) are 152 MB
                 "traffic": 9.12e7,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                if peaks else "fallback 1.4 PFLOP/s sustained",
@@ -334,7 +339,13 @@ def main():
                 "per_class_ms": {k: round(v[0], 3) for k, v in kt.items()},
                 "per_class_tflops": {k: (v[2] / (v[0] * 1e-3) / 1e12 if v[0] > 0 else 0.0) for k, v in kt.items()},
                 "step_tflops": flops_per_step(S) / (ms_per_step * 1e-3) / 1e12,
-                "step_frac_of_peak": flops_per_step(S) / (ms_per_step * 1e-3) / 1e12 / peak}
+                "step_frac_of_peak": flops_per_step(S) / (ms_per_step * 1e-3) / 1e12 / peak,
+                # what actually bounds this kernel: one exponential per 128 tensor FLOPs (head dim 32).  MUFU alone
+                # retires 15.9 ex2 / clk / SM (profiles/r1_pipe_rates_microbench.txt); the kernel splits the
+                # exponentials between MUFU and the FMA pipes
+                "exponentials": {"achieved_per_s": achieved * 1e12 / 128.0,
+                                 "mufu_only_peak_per_s": 15.9 * 148 * 1.965e9,
+                                 "frac_of_mufu_only_peak": achieved * 1e12 / 128.0 / (15.9 * 148 * 1.965e9)}}
 
     if rank == 0:
         cpu = None

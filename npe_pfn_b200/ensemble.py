@@ -242,8 +242,11 @@ class EnsembleDim:
                     k = max(1, min(N // 10 + 1, n_el // 2))
                     scale = base.std(dim=0, unbiased=False)
                     scale = torch.where(scale == 0, torch.ones_like(scale), scale)
-                    _u, _s, vt = torch.linalg.svd(base / scale, full_matrices=False)
-                    vt = vt[:k]
+                    # right singular vectors of the scaled base matrix = eigenvectors of its small Gram matrix
+                    # (n_el x n_el, fp64): much cheaper on the device than an SVD of the tall [N, n_el] matrix
+                    Z = base / scale
+                    _w, vecs = torch.linalg.eigh(Z.t() @ Z)
+                    vt = vecs.flip(1).t()[:k].contiguous()
                     big = vt.abs().argmax(dim=1)
                     sign = torch.sign(vt[torch.arange(k, device=dev), big])
                     sign = torch.where(sign == 0, torch.ones_like(sign), sign)
