@@ -65,8 +65,9 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
 int pfn_ctx_destroy(pfn_ctx* ctx);
 /* runtime switches (no reference counterpart): "attn_impl" / "gemm_impl" 0 = warp-level mma.sync kernels,
  * 1 = tcgen05/TMEM/TMA kernels (default); "chunk_rows" = test rows per pass; "standardize_y" 0 = targets enter the y-encoder unscaled (classifier head:
- * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes; "attn_lean" 1 (default) = reference maximum folded
- * into the Q K^T MMA + overflow check instead of the maximum pass, 0 = explicit maximum pass per tile; "time_kernels" 1 = record a
+ * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes; "attn_lean" 2 (default) / 1 = reference maximum folded
+ * into the Q K^T MMA + overflow check instead of the maximum pass (1: every reference change redoes / slows the warp's tile, 2: kept on the
+ * fast path), 0 = explicit maximum pass per tile; "time_kernels" 1 = record a
  * CUDA event pair around every attention / GEMM launch on its stream (read back with pfn_kernel_times). */
 int pfn_set_option(pfn_ctx* ctx, const char* key, int64_t value);
 

@@ -482,9 +482,43 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 const float baked = LEAN ? (b ? mb1 : mb0) : 0.f;
                 uint32_t pk[kTwo ? 32 : 16];
                 bool fast = false;
+                // publish a new reference for the tiles whose Q K^T has not been issued yet (j + 2 onwards).  Q K_{j+1}^T
+                // may still be reading the old value: wait for its completion barrier first.
+                auto publish = [&](float m) {
+                    if (j + 1 < ntiles) mbar_wait(bar_s + 8 * (b ^ 1u), ((g + 1u) >> 1) & 1u);
+                    const float hi = 256.0f * rintf(m * (1.0f / 256.0f));
+                    *reinterpret_cast<uint32_t*>(qx_row) = pack_bf16x2(-hi, -(m - hi));
+                    m_q = m;
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                };
                 if constexpr (LEAN && kTwo) {
-                    fast = __all_sync(0xffffffffu, j > 0 && nvalid == TC_BN && baked == m_cur);
+                    // LEAN 1: any row whose baked reference differs from m_cur sends the warp to the general path.
+                    // LEAN 2: a row that only LAGS behind a reference it published itself (m_cur != m_q) adopts the
+                    //         baked value with one rescale of O and l and stays on the fast path.
+                    const bool stale = baked != m_cur && (LEAN == 1 || m_cur == m_q);
+                    fast = !__any_sync(0xffffffffu, j == 0 || nvalid != TC_BN || stale);
                     if (fast) {
+                        if constexpr (LEAN == 2) {
+                            const bool adopt = baked != m_cur;
+                            if (__any_sync(0xffffffffu, adopt)) {
+                                float corr = 1.0f;
+                                if (adopt) {
+                                    corr = fast_exp2(m_cur - baked);
+                                    float l0, l1;
+                                    upk2(l2, l0, l1);
+                                    l2 = pk2(l0 * corr, l1 * corr);
+                                    m_cur = baked;
+                                }
+                                mbar_wait(bar_pv, (g - 1u) & 1u);  // O += P_{j-1} V_{j-1} must have landed
+                                tc_fence_after();
+                                uint32_t ov[32];
+                                tmem_ld32(orow, ov);
+                                tmem_wait_ld();
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) ov[i] = __float_as_uint(__uint_as_float(ov[i]) * corr);
+                                tmem_st32(orow, ov);
+                            }
+                        }
                         uint32_t sa[32], ovf = 0;
                         uint64_t l2n = l2;
                         tmem_ld32(scol, sa);
@@ -494,8 +528,29 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         tmem_wait_ld();
                         softmax_exp32_lean<POLY16, DEG>(sa, pk + 16, l2n, ovf);
                         if (__any_sync(0xffffffffu, (ovf & 0xC000C000u) != 0u)) {
-                            fast = false;  // redo below (S is intact)
-                            if (p.dbg && lane == 0) atomicAdd(p.dbg + 0, 1ull);
+                            // some P >= 2 (or an exponent wrapped): rare.  LEAN 1 redoes the tile on the general path.
+                            // LEAN 2 looks at the row's largest P: below 2^64 the tile is kept as it is (P is only
+                            // large, not wrong) and a higher reference is published for two tiles ahead; otherwise redo.
+                            bool redo = true;
+                            if constexpr (LEAN == 2) {
+                                uint32_t mx = 0;
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) mx = max(mx, max(pk[i] & 0xffffu, pk[i] >> 16));
+                                redo = __any_sync(0xffffffffu, mx >= 0x5F80u);  // >= 2^64, inf, NaN or sign bit
+                                if (!redo && mx >= 0x4000u) {
+                                    const float m_new = m_cur + (float)((int)(mx >> 7) - 127 + 8);
+                                    if (m_new > m_q) {
+                                        publish(m_new);
+                                        if (p.dbg) atomicAdd(p.dbg + 1, 1ull);
+                                    }
+                                }
+                            }
+                            if (redo) {
+                                fast = false;  // S is still intact in TMEM
+                                if (p.dbg && lane == 0) atomicAdd(p.dbg + 0, 1ull);
+                            } else {
+                                l2 = l2n;
+                            }
                         } else {
                             l2 = l2n;
                         }
@@ -568,15 +623,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                         }
                         softmax_exp32<POLY16, DEG>(sa, pk + 16, sc, -delta, cm, smin, l2);
                     }
-                    if (LEAN && m_cur != m_q) {
-                        // publish the new reference for the tiles whose Q K^T has not been issued yet (j + 2 onwards).
-                        // Q K_{j+1}^T may still be reading the old value: wait for its completion barrier first.
-                        if (j + 1 < ntiles) mbar_wait(bar_s + 8 * (b ^ 1u), ((g + 1u) >> 1) & 1u);
-                        const float hi = 256.0f * rintf(m_cur * (1.0f / 256.0f));
-                        *reinterpret_cast<uint32_t*>(qx_row) = pack_bf16x2(-hi, -(m_cur - hi));
-                        m_q = m_cur;
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    }
+                    if (LEAN && need && m_cur != m_q) publish(m_cur);  // only a reference changed HERE is published (a
+                                                                       // lagging LEAN-2 row keeps its pending, higher one)
                 }
                 if constexpr (kTwo) tmem_st32(scol, reinterpret_cast<uint32_t(&)[32]>(pk));
                 else tmem_st16(scol, pk);
@@ -707,6 +755,10 @@ static inline cudaError_t launch_attn_tc(const AttnArgs& a, int heads, int T, in
         PFN_ATTN_CASE(0) PFN_ATTN_CASE(3) PFN_ATTN_CASE(4) PFN_ATTN_CASE(5) PFN_ATTN_CASE(6) PFN_ATTN_CASE(7) PFN_ATTN_CASE(8)
         case 106: return launch_attn_tc_impl<6, 2, 0>(mq, mkv, p, grid, st);
         case 1106: return launch_attn_tc_impl<6, 2, 1>(mq, mkv, p, grid, st);
+        case 2004: return launch_attn_tc_impl<4, 3, 2>(mq, mkv, p, grid, st);
+        case 2005: return launch_attn_tc_impl<5, 3, 2>(mq, mkv, p, grid, st);
+        case 2006: return launch_attn_tc_impl<6, 3, 2>(mq, mkv, p, grid, st);
+        case 2000: return launch_attn_tc_impl<0, 3, 2>(mq, mkv, p, grid, st);
         default: return cudaErrorInvalidValue;
     }
 #undef PFN_ATTN_CASE

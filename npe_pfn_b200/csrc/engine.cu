@@ -93,7 +93,8 @@ struct pfn_ctx {
     int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
     int attn_debug = 0;                      // count reference-change events of the item-attention kernel
     unsigned long long* attn_dbg = nullptr;  // [3] device counters (attn_tc.cuh::TcArgs::dbg)
-    int attn_lean = 1;  // 1: reference maximum folded into the QK^T MMA, overflow check instead of the maximum pass (attn_tc v5)
+    int attn_lean = 2;  // 1/2: reference maximum folded into the QK^T MMA, overflow check instead of the maximum pass (attn_tc v5);
+                        // 2: rows lagging behind a reference they published adopt it on the fast path, large-but-finite P tiles are kept
     int attn_poly = 5;  // k of every 16 pairs of exponentials on the FMA pipes (+100: degree-2 polynomial); 0 = all on MUFU. r1 sweep: 0 -> 437, 5 -> 473 TFLOP/s
     int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
@@ -198,7 +199,7 @@ int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
     TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
 #ifdef PFN_WITH_ATTN_TC
     if (c->attn_impl == 1) {
-        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly + 1000 * (c->attn_lean && !c->attn_persist), c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns,
+        PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly + 1000 * (c->attn_persist ? 0 : c->attn_lean), c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns,
                                        c->attn_debug ? c->attn_dbg : nullptr, st));
     } else
 #endif

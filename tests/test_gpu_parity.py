@@ -579,7 +579,8 @@ def test_item_attention_sharp_scores(weights, gain):
     Xt = torch.randn(M, F, generator=g)
     outs = {}
     for name, opts in {"mma": {"attn_impl": 0}, "v4": {"attn_impl": 1, "attn_lean": 0}, "v5": {"attn_impl": 1, "attn_lean": 1},
-                       "v5_mufu": {"attn_impl": 1, "attn_lean": 1, "attn_poly": 0}}.items():
+                       "v5_mufu": {"attn_impl": 1, "attn_lean": 1, "attn_poly": 0},
+                       "v5b": {"attn_impl": 1, "attn_lean": 2}}.items():
         eng.set_option("attn_poly", 5)
         for k, v in opts.items():
             eng.set_option(k, v)
@@ -591,7 +592,7 @@ def test_item_attention_sharp_scores(weights, gain):
             redo, changes, general = eng.attn_debug_counts()
             print(f"gain {gain} {name}: redone tiles {redo}, reference changes {changes}, general-path tiles {general}")
             assert changes > 0, "the test must exercise reference-maximum changes"
-            if name.startswith("v5"):
+            if name in ("v5", "v5_mufu"):
                 assert redo > 0, "the test must exercise the overflow check + redo path"
     ref = OracleTabPFNRegressor(weights=w).fit(Xc, yc).predict(Xt)["logits"]
     for name, o in outs.items():
@@ -600,7 +601,7 @@ def test_item_attention_sharp_scores(weights, gain):
     # the three tensor-core variants see the same bf16 operands: they agree with each other at least as well as the
     # mma.sync kernel agrees with the oracle
     base = (outs["mma"] - ref).abs()
-    for name in ("v4", "v5", "v5_mufu"):
+    for name in ("v4", "v5", "v5_mufu", "v5b"):
         d = (outs[name] - ref).abs()
         assert d.max() <= max(2.0 * base.max(), LOGIT_ATOL) and d.mean() <= max(1.5 * base.mean(), LOGIT_MEAN_ATOL), name
     # direct comparison on identical bf16 operands: v5 is as close to the mma.sync kernel as v4 is (differences come from
@@ -609,4 +610,7 @@ def test_item_attention_sharp_scores(weights, gain):
     d5 = (outs["v5"] - outs["mma"]).abs()
     print(f"gain {gain}: v4 vs mma max {d4.max():.4f} mean {d4.mean():.5f} | v5 vs mma max {d5.max():.4f} mean {d5.mean():.5f}")
     assert d5.mean() <= 1.5 * d4.mean() + 0.01
+    d5b = (outs["v5b"] - outs["mma"]).abs()
+    print(f"gain {gain}: v5b vs mma max {d5b.max():.4f} mean {d5b.mean():.5f}")
+    assert d5b.mean() <= 1.5 * d4.mean() + 0.01
     eng.close()

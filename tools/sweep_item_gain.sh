@@ -1,4 +1,4 @@
-for g in 2.5 6; do for l in 0 1; do
+for g in 1 2.5 6; do for l in 1 2; do
 python bench.py --steps 1 --warmup 1 --samples 37888 --no-cpu-baseline --item-gain $g --opt attn_lean=$l --opt attn_debug=1 > gpurun_out/r56_g${g}_l$l.log 2>&1
 python - <<PY
 import json
