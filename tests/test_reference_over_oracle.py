@@ -107,3 +107,26 @@ def test_reference_density_ratio_wrapper_equals_mirror(ref_pkg):
         assert ref.refit_necessary(*args) == mine.refit_necessary(*args)
     a, b = ref.ratio_log_probs(th, 1e-15), mine.ratio_log_probs(th, 1e-15)
     assert torch.allclose(a, b, atol=1e-6) and torch.isfinite(a).all()
+
+
+def test_reference_loops_over_the_ensemble_oracle(ref_pkg, weights):
+    """The unmodified reference with `regressor_init_kwargs={"n_estimators": 2}` (upstream's ensemble switch) over the
+    ensemble oracle equals the restated loops over the same oracle: the five-call protocol carries the ensemble
+    unchanged (logits = log of the member-averaged probabilities, criterion on the common borders)."""
+    pkg, core = ref_pkg
+    from oracle.ensemble import OracleEnsembleRegressor
+    from oracle.reference_loop import logprob_loop, sample_loop
+    theta, x, g = _toy(40, 2, 2, 5)
+    xo = x[:1].clone()
+    kw = {"n_estimators": 2, "weights": weights, "random_state": 4}
+    post = core.NPE_PFN_Core(prior=torch.distributions.MultivariateNormal(torch.zeros(2), torch.eye(2)),
+                             regressor_init_kwargs=kw)
+    assert type(post._model).__name__ == "OracleEnsembleRegressor"
+    post.append_simulations(theta, x)
+    torch.manual_seed(3)
+    s_ref, lp_ref = post._sample(6, xo, with_log_prob=True)
+    torch.manual_seed(3)
+    s_me, lp_me = sample_loop(OracleEnsembleRegressor(**kw), x, theta, xo, 6, with_log_prob=True)
+    assert torch.equal(s_ref, s_me) and torch.allclose(lp_ref, lp_me, atol=1e-6)
+    th = torch.randn(5, 2, generator=g)
+    assert torch.allclose(post.log_prob(th, xo), logprob_loop(OracleEnsembleRegressor(**kw), x, theta, xo, th), atol=1e-6)
