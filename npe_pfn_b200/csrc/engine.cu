@@ -22,6 +22,7 @@
 #include "gemm_mma.cuh"
 #ifdef PFN_WITH_ATTN_TC
 #include "gemm_tc.cuh"
+#include "mlp_tc.cuh"
 #endif
 #include "small_kernels.cuh"
 #include "filter_kernels.cuh"
@@ -91,6 +92,7 @@ struct pfn_ctx {
     int attn_wait_ticks = 1000;
     int attn_stagger_ns = 0;
     int standardize_y = 1;  // 0 for the classifier head (targets are class indices)
+    int mlp_fused = 1;  // 1: MLP sub-layer (up-projection, GELU, down-projection, residual, LayerNorm) in one kernel (mlp_tc.cuh)
     int attn_debug = 0;                      // count reference-change events of the item-attention kernel
     unsigned long long* attn_dbg = nullptr;  // [3] device counters (attn_tc.cuh::TcArgs::dbg)
     int attn_lean = 2;  // 1/2: reference maximum folded into the QK^T MMA, overflow check instead of the maximum pass (attn_tc v5);
@@ -289,6 +291,15 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
         g.A = c->ob + off; g.lda = ld; g.W = wb + o.item_wo + (size_t)l * kE * kE; g.M = rows; g.N = kE; g.K = kE;
         g.Cb = c->xb + off; g.ldcb = ld; g.Cf = c->xf + off; g.ldcf = ld;
         if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
+#ifdef PFN_WITH_ATTN_TC
+        if (c->gemm_impl == 1 && c->mlp_fused) {
+            TimeScope ts(c, st, KC_GEMM, 4.0 * (double)rows * kHid * kE);
+            PFN_CUDA_OK(launch_mlp_tc(c->xb + off, ld, wb + o.mlp_w1 + (size_t)l * kHid * kE, wb + o.mlp_w2 + (size_t)l * kE * kHid,
+                                      c->xb + off, ld, c->xf + off, ld, rows, c->cfg.ln_eps, c->num_sms, st));
+            c->launches++;
+            return 0;
+        }
+#endif
         g.A = c->xb + off; g.lda = ld; g.W = wb + o.mlp_w1 + (size_t)l * kHid * kE; g.N = kHid; g.K = kE;
         g.Cb = c->hb_s; g.ldcb = kHid; g.Cf = nullptr; g.bias = nullptr;
         if (int rc = gemm<EPI_BIAS_GELU_BF16>(c, g, st)) return rc;
@@ -403,6 +414,7 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
     if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
     if (const char* e = getenv("NPE_PFN_B200_GEMM")) c->gemm_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
     if (const char* e = getenv("NPE_PFN_B200_ATTN_LEAN")) c->attn_lean = atoi(e);
+    if (const char* e = getenv("NPE_PFN_B200_MLP_FUSED")) c->mlp_fused = atoi(e);
     if (const char* e = getenv("NPE_PFN_B200_ATTN_POLY")) {  // tuning / parity sweeps of the exponential split
         if (int rc = pfn_set_option(c, "attn_poly", atoll(e))) { delete c; return rc; }
     }
@@ -455,6 +467,7 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_wait_ticks")) { c->attn_wait_ticks = (int)value; return 0; }
     if (!strcmp(key, "attn_stagger_ns")) { c->attn_stagger_ns = (int)value; return 0; }
     if (!strcmp(key, "attn_lean")) { c->attn_lean = (int)value; return 0; }
+    if (!strcmp(key, "mlp_fused")) { c->mlp_fused = (int)value; return 0; }
     if (!strcmp(key, "attn_debug")) {
         if (value && !c->attn_dbg) PFN_CUDA_OK(cudaMalloc(&c->attn_dbg, 3 * sizeof(unsigned long long)));
         if (value) PFN_CUDA_OK(cudaMemset(c->attn_dbg, 0, 3 * sizeof(unsigned long long)));

@@ -614,3 +614,24 @@ def test_item_attention_sharp_scores(weights, gain):
     print(f"gain {gain}: v5b vs mma max {d5b.max():.4f} mean {d5b.mean():.5f}")
     assert d5b.mean() <= 1.5 * d4.mean() + 0.01
     eng.close()
+
+
+def test_fused_mlp_kernel_agrees(engine):
+    """The fused MLP kernel (mlp_tc.cuh: up-projection, GELU, down-projection, residual, LayerNorm in one launch) against
+    the two-kernel tcgen05 path: same bf16 operands and fp32 accumulation, the hidden activation is rounded to bf16 in
+    both, so logits agree to rounding noise."""
+    g = torch.Generator().manual_seed(55)
+    outs = {}
+    for (N, F, M) in ((700, 6, 900), (130, 3, 257)):
+        Xc = torch.randn(N, F, generator=g)
+        yc = Xc[:, 2] - Xc[:, 0] + 0.1 * torch.randn(N, generator=g)
+        Xt = torch.randn(M, F, generator=g)
+        for fused in (0, 1):
+            engine.set_option("mlp_fused", fused)
+            engine.prefill(6, Xc, yc)
+            outs[fused] = engine.forward_logits(6, Xt)
+        engine.set_option("mlp_fused", 1)
+        d = (outs[0] - outs[1]).abs()
+        print(f"fused vs two-kernel MLP (N={N}): max|dlogit|={d.max():.4f} mean={d.mean():.5f}")
+        assert torch.isfinite(outs[1]).all()
+        assert d.max() <= 0.1 and d.mean() <= 0.01
