@@ -265,9 +265,9 @@ __device__ __forceinline__ void softmax_exp32(const uint32_t (&s)[32], uint32_t*
 
 // "Lean" form: the scores arrive as x = s - m already (scale folded into the Q projection, -m contributed by the
 // third K = 16 block of the Q K^T MMA), so a MUFU pair is two ex2 and nothing else, and the tile maximum is replaced by
-// an overflow check: `ovf` ORs every packed bf16 pair; sign or top exponent bit set (mask 0xC000C000) <=> some P >= 2
-// (or an overflowed FMA-form exponent) <=> a score exceeded the reference by >= 1, and the caller redoes the tile on
-// the general path.
+// an overflow check: the tile's own row sum (accumulated from zero) reaching 2 <=> some P >= 2 is possible <=> a score
+// may have exceeded the reference by >= 1 (a NaN sum counts as overflow); `ovf` ORs the packed pairs of the FMA form,
+// whose exponent can wrap into the sign bit (mask 0x80008000).  The caller then redoes / re-references the tile.
 template <int POLY16, int DEG>
 __device__ __forceinline__ void softmax_exp32_lean(const uint32_t (&s)[32], uint32_t* pk, uint64_t& l2, uint32_t& ovf) {
     const uint64_t CM = pk2(kExpMagic, kExpMagic), NEG1 = pk2(-1.0f, -1.0f);
@@ -299,7 +299,7 @@ __device__ __forceinline__ void softmax_exp32_lean(const uint32_t (&s)[32], uint
         }
         l2 = fadd2(l2, pk2(p0, p1));
         pk[i] = pack_bf16x2(p0, p1);
-        ovf |= pk[i];
+        if (poly) ovf |= pk[i];  // only the FMA form can wrap its exponent into the sign bit; P >= 2 shows in the tile sum
     }
 }
 
@@ -520,14 +520,17 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                             }
                         }
                         uint32_t sa[32], ovf = 0;
-                        uint64_t l2n = l2;
+                        uint64_t lt2 = 0;  // this tile's row sum, from zero
                         tmem_ld32(scol, sa);
                         tmem_wait_ld();
-                        softmax_exp32_lean<POLY16, DEG>(sa, pk, l2n, ovf);
+                        softmax_exp32_lean<POLY16, DEG>(sa, pk, lt2, ovf);
                         tmem_ld32(scol + 32, sa);
                         tmem_wait_ld();
-                        softmax_exp32_lean<POLY16, DEG>(sa, pk + 16, l2n, ovf);
-                        if (__any_sync(0xffffffffu, (ovf & 0xC000C000u) != 0u)) {
+                        softmax_exp32_lean<POLY16, DEG>(sa, pk + 16, lt2, ovf);
+                        float ts0, ts1;
+                        upk2(lt2, ts0, ts1);
+                        const uint64_t l2n = fadd2(l2, lt2);
+                        if (__any_sync(0xffffffffu, !(ts0 + ts1 < 2.0f) || (ovf & 0x80008000u) != 0u)) {
                             // some P >= 2 (or an exponent wrapped): rare.  LEAN 1 redoes the tile on the general path.
                             // LEAN 2 looks at the row's largest P: below 2^64 the tile is kept as it is (P is only
                             // large, not wrong) and a higher reference is published for two tiles ahead; otherwise redo.
