@@ -329,9 +329,10 @@ def main():
     tot_ms = sum(v[0] for v in kt.values())
     roofline = {"bound": "tensor", "kernel": "item attention of test rows vs cached K/V", "achieved": achieved,
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-                # DRAM bytes per launch from ncu (profiles/r1_launch_summary_v4.csv: 149 attn_tc launches read
-                # 11 658 MB and wrote 1 903 MB); algorithmic bytes of the largest launch (Q in, O out, K/V) are 152 MB
-                "traffic": 9.12e7,
+                # DRAM bytes per launch from ncu (profiles/r1_launch_summary_v5_fused.csv: 167 attn_tc launches of 16 384
+                # query rows read 12 393 MB and wrote 2 048 MB = 86.5 MB per launch; Q in + O out are 2 x 384 B per token,
+                # the K/V tiles are L2 hits), scaled to this run's rows per launch (the library's chunk of 37 888 rows)
+                "traffic": 8.65e7 * min(S, 37888) / 16384.0,
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches": a_cnt, "avg_launch_ms": a_ms / max(a_cnt, 1),
