@@ -1,22 +1,67 @@
-"""Rejection loop of `/root/reference/npe_pfn/accept_reject_sampler.py:8-91`, same semantics:
-first batch `min(num_samples, max_bs)`, then `min(max_bs, max(int(1.5 * remaining / acc), 100))`,
-keep the FIRST `num_samples` accepted rows in proposal order, return a 3-tuple
-`(samples, log_probs | None, acceptance_rate)`; when `max_iter_rejection` is exceeded the last
-unfiltered candidate batch is appended (Appendix B.3 of SURVEY.md).
+"""Prior-support rejection around the autoregressive sampler.
 
-Works on whatever device the proposal returns (CUDA tensors from the B200 path stay on the device;
-the only host synchronisation per round is the accepted count, as in the reference's `.sum().item()`).
-`accept_reject_fn` may return either a boolean mask or, for the fused device path, a callable
-attribute `compact(candidates, log_probs)` is used when present (support check + ordered compaction
-in one kernel chain, `pfn_accept_compact`).
+Semantics follow `/root/reference/npe_pfn/accept_reject_sampler.py:8-91`: the first round
+proposes `min(num_samples, max_bs)` rows, later rounds `min(max_bs, max(int(1.5 * missing / rate), 100))`; the FIRST
+`num_samples` accepted rows are returned in proposal order together with their log-probs (or None) and the overall
+acceptance rate; once `max_iter_rejection` rounds have passed, the last round's UNFILTERED proposals are appended and the
+loop stops.
+
+The loop itself is organised around a small ledger object; tensors stay on the device the proposal returned them on.
+When the acceptance function carries a `compact(candidates, log_probs)` attribute (the engine's support check +
+ordered stream compaction, `pfn_accept_compact`), a round costs one kernel chain and one scalar read-back — the same
+single host synchronisation per round the reference has in `.sum().item()`.
 """
 from __future__ import annotations
 
-from typing import Callable, Dict, Optional, Tuple
+from dataclasses import dataclass, field
+from typing import Callable, Dict, List, Optional, Tuple
 
 import torch
 from torch import Tensor
 from tqdm import tqdm
+
+_MIN_ROUND = 100      # smallest follow-up round
+_OVERDRAW = 1.5       # safety factor on the expected number of proposals still needed
+
+
+def next_round_size(missing: int, proposed: int, kept: int, cap: int) -> int:
+    """Rows to propose next, from the running acceptance rate (`accept_reject_sampler.py:64-72` of the reference)."""
+    rate = max(kept / proposed, 1e-12)
+    return min(cap, max(int(_OVERDRAW * missing / rate), _MIN_ROUND))
+
+
+@dataclass
+class _Ledger:
+    wanted: int
+    rows: List[Tensor] = field(default_factory=list)
+    logps: List[Tensor] = field(default_factory=list)
+    proposed: int = 0
+    kept: int = 0
+
+    @property
+    def missing(self) -> int:
+        return self.wanted - self.kept
+
+    def book(self, rows: Tensor, logp: Optional[Tensor], n_proposed: int, n_kept: int) -> None:
+        self.rows.append(rows)
+        if logp is not None:
+            self.logps.append(logp)
+        self.proposed += n_proposed
+        self.kept += n_kept
+
+    def result(self) -> Tuple[Tensor, Optional[Tensor], float]:
+        out = torch.cat(self.rows, dim=0)[:self.wanted]
+        lp = torch.cat(self.logps, dim=0)[:self.wanted] if self.logps else None
+        return out, lp, len(out) / max(self.proposed, 1)
+
+
+def _filter_round(accept_reject_fn: Callable, cand: Tensor, logp: Optional[Tensor]):
+    """-> (kept rows, kept log-probs | None, number kept) for one round of proposals."""
+    fused = getattr(accept_reject_fn, "compact", None)
+    if fused is not None and cand.is_cuda:
+        return fused(cand, logp)
+    mask = accept_reject_fn(cand)
+    return cand[mask], (None if logp is None else logp[mask]), int(mask.sum().item())
 
 
 @torch.no_grad()
@@ -29,47 +74,20 @@ def accept_reject_sample(
     proposal_sampling_kwargs: Optional[Dict] = None,
     max_iter_rejection: int | None = None,
 ) -> Tuple[Tensor, Optional[Tensor], float]:
-    if proposal_sampling_kwargs is None:
-        proposal_sampling_kwargs = {}
-    pbar = tqdm(disable=not show_progress_bars, total=num_samples, desc=f"Drawing {num_samples} posterior samples")
-
-    accepted, accepted_log_probs = [], []
-    num_remaining = num_samples
-    num_sampled_total = 0
-    num_accepted_total = 0
-    sampling_batch_size = min(num_samples, max_sampling_batch_size)
-    i = 0
-    compact = getattr(accept_reject_fn, "compact", None)
-    while num_remaining > 0:
-        i += 1
-        candidates, log_probs = proposal(sampling_batch_size, **proposal_sampling_kwargs)
-        if compact is not None and candidates.is_cuda:
-            kept, kept_lp, num_accepted = compact(candidates, log_probs)
-            accepted.append(kept)
-            if log_probs is not None:
-                accepted_log_probs.append(kept_lp)
-        else:
-            are_accepted = accept_reject_fn(candidates)
-            accepted.append(candidates[are_accepted])
-            if log_probs is not None:
-                accepted_log_probs.append(log_probs[are_accepted])
-            num_accepted = int(are_accepted.sum().item())
-        num_sampled_total += sampling_batch_size
-        num_accepted_total += num_accepted
-        num_remaining -= num_accepted
-        pbar.update(num_accepted)
-
-        acceptance_rate = num_accepted_total / num_sampled_total
-        sampling_batch_size = min(max_sampling_batch_size,
-                                  max(int(1.5 * num_remaining / max(acceptance_rate, 1e-12)), 100))
-        if max_iter_rejection is not None and i > max_iter_rejection:
-            accepted.append(candidates)
-            if log_probs is not None:
-                accepted_log_probs.append(log_probs)
+    kwargs = proposal_sampling_kwargs or {}
+    ledger = _Ledger(wanted=num_samples)
+    bar = tqdm(disable=not show_progress_bars, total=num_samples, desc=f"Drawing {num_samples} posterior samples")
+    round_size = min(num_samples, max_sampling_batch_size)
+    rounds = 0
+    while ledger.missing > 0:
+        rounds += 1
+        cand, logp = proposal(round_size, **kwargs)
+        kept_rows, kept_logp, n_kept = _filter_round(accept_reject_fn, cand, logp)
+        ledger.book(kept_rows, kept_logp, round_size, n_kept)
+        bar.update(n_kept)
+        round_size = next_round_size(ledger.missing, ledger.proposed, ledger.kept, max_sampling_batch_size)
+        if max_iter_rejection is not None and rounds > max_iter_rejection:
+            ledger.book(cand, logp, 0, 0)  # give up filtering: hand back the raw proposals of this round
             break
-    pbar.close()
-
-    samples = torch.cat(accepted, dim=0)[:num_samples]
-    log_probs = torch.cat(accepted_log_probs, dim=0)[:num_samples] if accepted_log_probs else None
-    final_acceptance_rate = len(samples) / max(num_sampled_total, 1)
-    return samples, log_probs, final_acceptance_rate
+    bar.close()
+    return ledger.result()
