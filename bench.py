@@ -344,6 +344,10 @@ def main():
                 # what actually bounds this kernel: one exponential per 128 tensor FLOPs (head dim 32).  MUFU alone
                 # retires 15.9 ex2 / clk / SM (profiles/r1_pipe_rates_microbench.txt); the kernel splits the
                 # exponentials between MUFU and the FMA pipes
+                # the fused MLP sub-layer (mlp_tc.cuh) is the step's dense-GEMM kernel proper: 4 * tokens * 192 * 768 FLOPs per launch
+                "mlp_kernel": ({"achieved": kt["mlp"][2] / (kt["mlp"][0] * 1e-3) / 1e12, "unit": "TFLOP/s",
+                                "frac": kt["mlp"][2] / (kt["mlp"][0] * 1e-3) / 1e12 / peak, "launches": kt["mlp"][1]}
+                               if kt.get("mlp", (0, 0, 0))[0] > 0 else None),
                 "exponentials": {"achieved_per_s": achieved * 1e12 / 128.0,
                                  "mufu_only_peak_per_s": 15.9 * 148 * 1.965e9,
                                  "frac_of_mufu_only_peak": achieved * 1e12 / 128.0 / (15.9 * 148 * 1.965e9)}}

@@ -126,8 +126,9 @@ int pfn_filter_context(pfn_ctx* ctx, const float* x_train, int64_t ld, int64_t N
 int pfn_slot_info(pfn_ctx* ctx, int slot, int64_t* N, int32_t* F, int32_t* T, int64_t* kv_bytes);
 /* number of kernels this library launched since creation (bench.py's gpu_launches) */
 int64_t pfn_launch_count(pfn_ctx* ctx);
-/* per-class device time of the launches recorded while "time_kernels" was on (host arrays of 4:
- * 0 = item attention of test rows, 1 = item attention of context rows, 2 = projection GEMMs, 3 = other):
+/* per-class device time of the launches recorded while "time_kernels" was on (host arrays of 5:
+ * 0 = item attention of test rows, 1 = item attention of context rows, 2 = projection GEMMs, 3 = other,
+ * 4 = fused MLP sub-layer):
  * summed milliseconds, launch counts and algorithmic FLOPs.  Synchronises the device. */
 int pfn_kernel_times(pfn_ctx* ctx, double* ms, int64_t* counts, double* flops, int reset);
 /* debug / parity: copy a slot's derived quantities to caller device buffers (any may be NULL):

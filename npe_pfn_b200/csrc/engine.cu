@@ -106,7 +106,7 @@ struct pfn_ctx {
     std::vector<cudaEvent_t> ev_pool;
 };
 
-enum KernelClass { KC_ATTN_TEST = 0, KC_ATTN_CTX = 1, KC_GEMM = 2, KC_OTHER = 3, KC_COUNT = 4 };
+enum KernelClass { KC_ATTN_TEST = 0, KC_ATTN_CTX = 1, KC_GEMM = 2, KC_OTHER = 3, KC_MLP = 4, KC_COUNT = 5 };
 
 namespace {
 
@@ -293,7 +293,7 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
         if (int rc = gemm<EPI_RESID_LN>(c, g, st)) return rc;
 #ifdef PFN_WITH_ATTN_TC
         if (c->gemm_impl == 1 && c->mlp_fused) {
-            TimeScope ts(c, st, KC_GEMM, 4.0 * (double)rows * kHid * kE);
+            TimeScope ts(c, st, KC_MLP, 4.0 * (double)rows * kHid * kE);
             PFN_CUDA_OK(launch_mlp_tc(c->xb + off, ld, wb + o.mlp_w1 + (size_t)l * kHid * kE, wb + o.mlp_w2 + (size_t)l * kE * kHid,
                                       c->xb + off, ld, c->xf + off, ld, rows, c->cfg.ln_eps, c->num_sms, st));
             c->launches++;

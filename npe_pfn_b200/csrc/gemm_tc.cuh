@@ -59,21 +59,33 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
     return d;
 }
 
-// erf by Abramowitz & Stegun 7.1.26 (|error| < 7e-7 in fp32): one rcp + one ex2 + 8 FMA-pipe operations
+// GELU with erf by Abramowitz & Stegun, arranged for few instructions:
+//   erf(|z|) = 1 - w,  w = (a1 t + a2 t^2 + ...) exp(-z^2),  t = 1 / (1 + p |z|),  z = x / sqrt(2)
+//   gelu(x)  = 0.5 x (1 + sign(x) erf|z|) = max(x, 0) - |x| (w / 2)
+// (the polynomial carries the factor 1/2, p and the exponent scale are expressed in x, so neither z nor a sign transfer
+// is ever formed).  PFN_GELU_TERMS = 3: formula 7.1.25, |erf error| <= 2.5e-5, i.e. |gelu error| <= 1.3e-5 |x| -- far
+// below the bf16 rounding (2^-9 relative) applied to every value this produces; one rcp, one ex2, 4 FFMA, 4 FMUL, 1 FMNMX.
+// PFN_GELU_TERMS = 5: formula 7.1.26, |erf error| < 7e-7 (two more FFMA).
+#ifndef PFN_GELU_TERMS
+#define PFN_GELU_TERMS 3
+#endif
 __device__ __forceinline__ float gelu_fast(float x) {
-    const float z = x * 0.70710678118654752440f;
-    const float a = fabsf(z);
-    float t;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.0f)));
-    float pl = fmaf(1.061405429f, t, -1.453152027f);
-    pl = fmaf(pl, t, 1.421413741f);
-    pl = fmaf(pl, t, -0.284496736f);
-    pl = fmaf(pl, t, 0.254829592f);
-    pl *= t;
-    const float e = fast_exp2(-a * a * 1.4426950408889634f);
-    const float erf_abs = fmaf(-pl, e, 1.0f);
-    const float erf = copysignf(erf_abs, z);
-    return 0.5f * x * (1.0f + erf);
+    const float ax = fabsf(x);
+    float t, q;
+#if PFN_GELU_TERMS == 5
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f * 0.70710678118654752440f, ax, 1.0f)));
+    q = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+    q = fmaf(q, t, 0.5f * 1.421413741f);
+    q = fmaf(q, t, 0.5f * -0.284496736f);
+    q = fmaf(q, t, 0.5f * 0.254829592f);
+#else
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.47047f * 0.70710678118654752440f, ax, 1.0f)));
+    q = fmaf(0.5f * 0.7478556f, t, 0.5f * -0.0958798f);
+    q = fmaf(q, t, 0.5f * 0.3480242f);
+#endif
+    const float e = fast_exp2((x * x) * (-0.5f * 1.4426950408889634f));  // exp(-x^2 / 2)
+    const float w = q * (t * e);
+    return fmaf(-ax, w, fmaxf(x, 0.0f));
 }
 
 // ---- epilogue: every global access goes through TMA on 32 x 32 sub-tiles staged in swizzled shared memory ----------

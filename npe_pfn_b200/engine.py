@@ -277,9 +277,9 @@ class Engine:
 
     def kernel_times(self, reset: bool = True):
         """{class: (ms, launches, flops)} of the launches recorded while option "time_kernels" was on."""
-        ms, cnt, fl = (c.c_double * 4)(), (c.c_int64 * 4)(), (c.c_double * 4)()
+        ms, cnt, fl = (c.c_double * 5)(), (c.c_int64 * 5)(), (c.c_double * 5)()
         self._check(self.lib.pfn_kernel_times(self._h, ms, cnt, fl, int(reset)))
-        names = ["attn_test", "attn_ctx", "gemm", "other"]
+        names = ["attn_test", "attn_ctx", "gemm", "other", "mlp"]
         return {n: (ms[i], cnt[i], fl[i]) for i, n in enumerate(names)}
 
     def filter_context(self, x_train: torch.Tensor, obs: torch.Tensor, k: int, want_dist: bool = False):

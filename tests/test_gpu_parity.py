@@ -558,18 +558,22 @@ def test_tsnpe_rounds_autoregressive(engine):
     assert s.shape == (50, 2) and bool(prior.support.check(s).all())
 
 
-@pytest.mark.parametrize("gain", [2.5, 6.0, 25.0])
-def test_item_attention_sharp_scores(weights, gain):
+@pytest.mark.parametrize("gain,nlayers", [(2.5, 12), (6.0, 2), (25.0, 2)])
+def test_item_attention_sharp_scores(weights, gain, nlayers):
     """Item attention with LARGE, sharply peaked scores (Q/K projections scaled up): the running maximum of a row keeps
     growing by more than 2^8 along the keys, so the tcgen05 kernel's reference-change machinery runs for real -- v5's
-    overflow check + redo, the stale tiles after a change, v4's lazy rescaling -- and must agree with the warp-level
-    mma.sync kernel (exact running maximum per tile) and with the fp32 oracle."""
+    overflow check + redo / re-reference, the stale tiles after a change, v4's lazy rescaling -- and must agree with the
+    warp-level mma.sync kernel (exact running maximum per tile) and with the fp32 oracle.  The two larger gains use a
+    2-layer model: with 12 layers of near-argmax attention the network is chaotic (any rounding difference grows to
+    ~0.4 in the logits, for every implementation), which would hide what this test is after."""
+    import dataclasses
     from npe_pfn_b200.engine import Engine
     from npe_pfn_b200.weights import PFNWeights
     from oracle.estimator import OracleTabPFNRegressor
-    t = {k: v.clone() for k, v in weights.t.items()}
-    t["item_wqkv"][:, :2 * weights.cfg.emsize] *= gain  # Q and K rows: scores grow by gain^2
-    w = PFNWeights(weights.cfg, t)
+    base_w = weights if nlayers == weights.cfg.nlayers else PFNWeights.random_init(dataclasses.replace(weights.cfg, nlayers=nlayers))
+    t = {k: v.clone() for k, v in base_w.t.items()}
+    t["item_wqkv"][:, :2 * base_w.cfg.emsize] *= gain  # Q and K rows: scores grow by gain^2
+    w = PFNWeights(base_w.cfg, t)
     eng = Engine(weights=w, max_slots=2)
     g = torch.Generator().manual_seed(int(gain))
     N, F, M = 1300, 3, 300
@@ -595,25 +599,21 @@ def test_item_attention_sharp_scores(weights, gain):
             if name in ("v5", "v5_mufu"):
                 assert redo > 0, "the test must exercise the overflow check + redo path"
     ref = OracleTabPFNRegressor(weights=w).fit(Xc, yc).predict(Xt)["logits"]
+    err = {}
     for name, o in outs.items():
         d = (o - ref).abs()
-        print(f"gain {gain} {name}: max|dlogit|={d.max():.4f} mean={d.mean():.5f}")
-    # the three tensor-core variants see the same bf16 operands: they agree with each other at least as well as the
-    # mma.sync kernel agrees with the oracle
-    base = (outs["mma"] - ref).abs()
+        err[name] = (float(d.max()), float(d.mean()))
+        print(f"gain {gain} L={nlayers} {name}: max|dlogit|={d.max():.4f} mean={d.mean():.5f}")
+    # every tensor-core variant is as close to the fp32 oracle as the mma.sync kernel is (same bf16 operands)
     for name in ("v4", "v5", "v5_mufu", "v5b"):
-        d = (outs[name] - ref).abs()
-        assert d.max() <= max(2.0 * base.max(), LOGIT_ATOL) and d.mean() <= max(1.5 * base.mean(), LOGIT_MEAN_ATOL), name
-    # direct comparison on identical bf16 operands: v5 is about as close to the mma.sync kernel as v4 is (differences come
-    # from P rounding / summation order / the FMA-pipe polynomial, amplified by 12 layers of sharp attention: at the
-    # larger gains the network is chaotic and any two variants sit ~0.3-0.5 apart, so the bound is a factor, not a match)
-    d4 = (outs["v4"] - outs["mma"]).abs()
-    d5 = (outs["v5"] - outs["mma"]).abs()
-    print(f"gain {gain}: v4 vs mma max {d4.max():.4f} mean {d4.mean():.5f} | v5 vs mma max {d5.max():.4f} mean {d5.mean():.5f}")
-    assert d5.mean() <= 2.0 * d4.mean() + 0.02
-    d5b = (outs["v5b"] - outs["mma"]).abs()
-    print(f"gain {gain}: v5b vs mma max {d5b.max():.4f} mean {d5b.mean():.5f}")
-    assert d5b.mean() <= 2.0 * d4.mean() + 0.02
+        assert err[name][0] <= max(2.0 * err["mma"][0], LOGIT_ATOL), (name, err)
+        assert err[name][1] <= max(1.5 * err["mma"][1], LOGIT_MEAN_ATOL), (name, err)
+    # and to the mma.sync kernel itself
+    d4 = (outs["v4"] - outs["mma"]).abs().mean()
+    for name in ("v5", "v5b"):
+        dn = (outs[name] - outs["mma"]).abs().mean()
+        print(f"gain {gain}: v4 vs mma {d4:.5f} | {name} vs mma {dn:.5f}")
+        assert dn <= 1.5 * d4 + 0.01, name
     eng.close()
 
 
