@@ -38,7 +38,7 @@
 extern "C" {
 #endif
 
-#define PFN_ABI_VERSION 1
+#define PFN_ABI_VERSION 2
 
 typedef struct pfn_ctx pfn_ctx; /* opaque */
 
@@ -86,14 +86,16 @@ int pfn_forward_logits(pfn_ctx* ctx, int slot, const float* X, int64_t ldx, int6
  * uniforms == NULL -> Philox4x32-10(seed; counter = (row0 + r, offset)).
  * Any of out_bin / out_u / out_logp may be NULL.  out_theta[r * ld_theta].
  * out_logp (if given) receives log p(theta_r) with -inf replaced by log(eps);
- * when `accumulate` != 0 it is added to the existing value. */
-int pfn_head_sample(pfn_ctx* ctx, int slot, const float* logits, int64_t ld_logits, int64_t M,
+ * when `accumulate` != 0 it is added to the existing value.
+ * Row r reads logits row r / group (group >= 1; ld_logits == 0: one row for all): `sample_batched` draws `group`
+ * samples per observation from that observation's dimension-0 logits (npe_pfn.py:199, 211-220) in ONE launch. */
+int pfn_head_sample(pfn_ctx* ctx, int slot, const float* logits, int64_t ld_logits, int64_t group, int64_t M,
                     const float* uniforms, uint64_t seed, uint64_t row0, uint64_t offset,
                     float* out_theta, int64_t ld_theta, int32_t* out_bin, float* out_u,
                     float* out_logp, float eps, int accumulate, void* stream);
 /* out_nll[r] = -log p(y_r) (may be +inf).  If out_logp != NULL it receives the
  * clamped log-prob as in pfn_head_sample. */
-int pfn_head_nll(pfn_ctx* ctx, int slot, const float* logits, int64_t ld_logits, int64_t M,
+int pfn_head_nll(pfn_ctx* ctx, int slot, const float* logits, int64_t ld_logits, int64_t group, int64_t M,
                  const float* y, int64_t ld_y, float* out_nll, float* out_logp, float eps,
                  int accumulate, void* stream);
 

@@ -543,29 +543,31 @@ int pfn_forward_logits(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_
     return 0;
 }
 
-int pfn_head_sample(pfn_ctx* c, int slot, const float* logits, int64_t ld_logits, int64_t M, const float* uniforms,
-                    uint64_t seed, uint64_t row0, uint64_t offset, float* out_theta, int64_t ld_theta, int32_t* out_bin,
+int pfn_head_sample(pfn_ctx* c, int slot, const float* logits, int64_t ld_logits, int64_t group, int64_t M,
+                    const float* uniforms, uint64_t seed, uint64_t row0, uint64_t offset, float* out_theta, int64_t ld_theta, int32_t* out_bin,
                     float* out_u, float* out_logp, float eps, int accumulate, void* stream) {
     if (int rc = check_slot(c, slot, true)) return rc;
     if (M == 0) return 0;
     PFN_REQUIRE(logits && out_theta, "null data pointer");
+    PFN_REQUIRE(group >= 1, "group must be >= 1");
     PFN_CUDA_OK(cudaSetDevice(c->device));
     HeadArgs h{};
-    h.logits = logits; h.ld_logits = ld_logits; h.M = M; h.B = c->cfg.num_buckets; h.borders = c->slots[slot].borders;
+    h.logits = logits; h.ld_logits = ld_logits; h.group = group; h.M = M; h.B = c->cfg.num_buckets; h.borders = c->slots[slot].borders;
     h.uniforms = uniforms; h.seed = seed; h.row0 = row0; h.offset = offset;
     h.out_theta = out_theta; h.ld_theta = ld_theta; h.out_bin = out_bin; h.out_u = out_u; h.out_logp = out_logp;
     h.log_eps = std::log((float)eps); h.accumulate = accumulate;
     return launch_head(c, h, true, (cudaStream_t)stream);
 }
 
-int pfn_head_nll(pfn_ctx* c, int slot, const float* logits, int64_t ld_logits, int64_t M, const float* y, int64_t ld_y,
+int pfn_head_nll(pfn_ctx* c, int slot, const float* logits, int64_t ld_logits, int64_t group, int64_t M, const float* y, int64_t ld_y,
                  float* out_nll, float* out_logp, float eps, int accumulate, void* stream) {
     if (int rc = check_slot(c, slot, true)) return rc;
     if (M == 0) return 0;
     PFN_REQUIRE(logits && y, "null data pointer");
+    PFN_REQUIRE(group >= 1, "group must be >= 1");
     PFN_CUDA_OK(cudaSetDevice(c->device));
     HeadArgs h{};
-    h.logits = logits; h.ld_logits = ld_logits; h.M = M; h.B = c->cfg.num_buckets; h.borders = c->slots[slot].borders;
+    h.logits = logits; h.ld_logits = ld_logits; h.group = group; h.M = M; h.B = c->cfg.num_buckets; h.borders = c->slots[slot].borders;
     h.y = y; h.ld_y = ld_y; h.out_nll = out_nll; h.out_logp = out_logp;
     h.log_eps = std::log((float)eps); h.accumulate = accumulate;
     return launch_head(c, h, false, (cudaStream_t)stream);
@@ -594,7 +596,7 @@ static int fused_step(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_t
             if (int rc = decode_rows(c, s, d0, n, c->logits, B, st)) return rc;
             const int64_t g0 = r0 + d0;
             HeadArgs h{};
-            h.logits = c->logits; h.ld_logits = B; h.M = n; h.B = B; h.borders = s.borders;
+            h.logits = c->logits; h.ld_logits = B; h.group = 1; h.M = n; h.B = B; h.borders = s.borders;
             h.log_eps = std::log((float)eps); h.accumulate = accumulate;
             h.out_logp = out_logp ? out_logp + g0 : nullptr;
             if (sample) {

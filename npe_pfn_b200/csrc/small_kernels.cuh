@@ -75,9 +75,10 @@ __global__ void __launch_bounds__(256) fit_stats_kernel(const float* __restrict_
         q += d * d;
     }
     q = block_sum_double(q, sh);
-    const double std_d = N > 1 ? sqrt(q / (double)(N - 1)) : 0.0;
+    // population standard deviation + 1e-20 like upstream's `np.std(y) + 1e-20`; a constant target keeps unit scale
+    const double std_d = sqrt(q / (double)N);
     float mean32 = (float)mean;
-    float std32 = (float)std_d;
+    float std32 = std_d > 0.0 ? (float)(std_d + 1e-20) : 0.f;
     if (!isfinite(std32) || std32 == 0.f) std32 = 1.f;
     if (!standardize_y) { mean32 = 0.f; std32 = 1.f; }  // classifier: class indices enter the y-encoder as they are
     double z = 0.0;
@@ -424,6 +425,7 @@ __device__ double bar_logp(const float* __restrict__ lg, int B, const float* __r
 struct HeadArgs {
     const float* logits;
     int64_t ld_logits;  // 0 = every row reads the same logits row
+    int64_t group;      // row r reads logits row r / group (sample_batched dimension 0: `group` draws per observation)
     int64_t M;
     int B;
     const float* borders;  // [B+1], original units
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(HeadArgs a) {
     float* row = head_smem + (size_t)warp * B;
     const double kLn2x40 = 40.0 * 0.6931471805599453;
     for (int64_t r = (int64_t)blockIdx.x * HEAD_WARPS + warp; r < a.M; r += (int64_t)gridDim.x * HEAD_WARPS) {
-        const float* lg = a.logits + r * a.ld_logits;
+        const float* lg = a.logits + (r / a.group) * a.ld_logits;
         __syncwarp();
         float m = -INFINITY;
         for (int i = lane; i < B; i += 32) {

@@ -35,6 +35,9 @@ ABI_SYMBOLS = [
     "pfn_debug_last_states", "pfn_member_transform", "pfn_ensemble_combine", "pfn_attn_debug_counts",
 ]
 
+#: PFN_ABI_VERSION of include/npe_pfn_b200.h this binding was written against
+ABI_VERSION = 2
+
 _LIB = None
 
 
@@ -47,12 +50,19 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     if path == _build.LIB_PATH and build_if_missing and _build.is_stale():
         try:
             _build.build_library()
-        except Exception as e:  # stale-but-present library is still usable; missing one is fatal
+        except Exception as e:  # a stale library may still be usable (the ABI check below decides); a missing one is fatal
             if not os.path.exists(path):
                 raise RuntimeError(f"libnpe_pfn_b200.so is missing and could not be built: {e}") from e
+            import warnings
+            warnings.warn(f"libnpe_pfn_b200.so is older than its sources and the rebuild failed ({e}); using the stale "
+                          f"library", RuntimeWarning)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found: run `python -c 'import __graft_entry__ as g; g.build()'`")
     L = ctypes.CDLL(path)
+    L.pfn_abi_version.restype = c.c_int
+    if L.pfn_abi_version() != ABI_VERSION:
+        raise RuntimeError(f"{path} exports ABI version {L.pfn_abi_version()}, this binding needs {ABI_VERSION}: rebuild "
+                           f"with `python -c 'import __graft_entry__ as g; g.build()'`")
     vp, i64, u64, i32, f32 = c.c_void_p, c.c_int64, c.c_uint64, c.c_int32, c.c_float
     L.pfn_abi_version.restype = c.c_int
     L.pfn_last_error.restype = c.c_char_p
@@ -67,9 +77,9 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_forward_logits.restype = c.c_int
     L.pfn_forward_logits.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp]
     L.pfn_head_sample.restype = c.c_int
-    L.pfn_head_sample.argtypes = [vp, c.c_int, vp, i64, i64, vp, u64, u64, u64, vp, i64, vp, vp, vp, f32, c.c_int, vp]
+    L.pfn_head_sample.argtypes = [vp, c.c_int, vp, i64, i64, i64, vp, u64, u64, u64, vp, i64, vp, vp, vp, f32, c.c_int, vp]
     L.pfn_head_nll.restype = c.c_int
-    L.pfn_head_nll.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp, vp, f32, c.c_int, vp]
+    L.pfn_head_nll.argtypes = [vp, c.c_int, vp, i64, i64, i64, vp, i64, vp, vp, f32, c.c_int, vp]
     L.pfn_sample.restype = c.c_int
     L.pfn_sample.argtypes = [vp, c.c_int, vp, i64, i64, vp, u64, u64, u64, vp, i64, vp, vp, f32, c.c_int, vp]
     L.pfn_logprob.restype = c.c_int
@@ -194,15 +204,16 @@ class Engine:
 
     def head_sample(self, slot: int, logits: torch.Tensor, M: Optional[int] = None, uniforms=None, seed=0, row0=0,
                     offset=0, out_theta=None, ld_theta=1, with_log_prob=False, out_logp=None, eps=1e-15,
-                    accumulate=False, return_bins=False, bins=None):
-        """logits [M, B] (or a single row broadcast to M rows when `M` is given and logits.shape[0] == 1)."""
+                    accumulate=False, return_bins=False, bins=None, group: int = 1):
+        """logits [M, B] (or a single row broadcast to M rows when `M` is given and logits.shape[0] == 1; or
+        logits [M / group, B] with `group` consecutive draws per logits row)."""
         logits = logits.to(self.device, torch.float32)
         assert logits.stride(-1) == 1
         if M is None:
             M = logits.shape[0]
             ld = logits.stride(0)
         else:
-            assert logits.shape[0] == 1 or logits.shape[0] == M
+            assert logits.shape[0] == 1 or logits.shape[0] * group == M
             ld = 0 if logits.shape[0] == 1 and M != 1 else logits.stride(0)
         if out_theta is None:
             out_theta = torch.empty(M, dtype=torch.float32, device=self.device)
@@ -213,7 +224,7 @@ class Engine:
             out_logp = torch.zeros(M, dtype=torch.float32, device=self.device)
         if uniforms is not None:
             uniforms = uniforms.to(self.device, torch.float32).contiguous()
-        self._check(self.lib.pfn_head_sample(self._h, slot, _ptr(logits), ld, M, _ptr(uniforms), seed, row0, offset,
+        self._check(self.lib.pfn_head_sample(self._h, slot, _ptr(logits), ld, int(group), M, _ptr(uniforms), seed, row0, offset,
                                              _ptr(out_theta), ld_theta, _ptr(bins), None, _ptr(out_logp), eps,
                                              int(accumulate), self._stream()))
         return out_theta, bins, out_logp
@@ -230,7 +241,7 @@ class Engine:
         ld = 0 if (logits.shape[0] == 1 and M != 1) else logits.stride(0)
         assert logits.shape[0] in (1, M)
         out = None if out_logp is not None else torch.empty(M, dtype=torch.float32, device=self.device)
-        self._check(self.lib.pfn_head_nll(self._h, slot, _ptr(logits), ld, M, _ptr(y), ld_y, _ptr(out), _ptr(out_logp), eps,
+        self._check(self.lib.pfn_head_nll(self._h, slot, _ptr(logits), ld, 1, M, _ptr(y), ld_y, _ptr(out), _ptr(out_logp), eps,
                                           int(accumulate), self._stream()))
         return out if out_logp is None else out_logp
 

@@ -200,9 +200,9 @@ class EnsembleDim:
         Xd = X.double()
         yd = y.double()
         y_mean = yd.mean()
-        y_std = yd.std(unbiased=True) if N > 1 else torch.zeros((), dtype=torch.float64, device=dev)
+        y_std = yd.std(unbiased=False) if N > 1 else torch.zeros((), dtype=torch.float64, device=dev)
         y_mean32 = y_mean.float()
-        y_std32 = y_std.float()
+        y_std32 = (y_std + 1e-20).float() if float(y_std) > 0 else torch.zeros((), dtype=torch.float32, device=dev)
         if not bool(torch.isfinite(y_std32)) or float(y_std32) == 0.0:
             y_std32 = torch.ones((), dtype=torch.float32, device=dev)
         yz = (y.float() - y_mean32) / y_std32

@@ -144,61 +144,106 @@ class PFNWeights:
     }
 
     @staticmethod
-    def load_checkpoint(path: str, cfg: Optional[PFNConfig] = None) -> "PFNWeights":
-        """Load a `tabpfn-v2-regressor.ckpt` (blind mapping, see `_CKPT_KEYMAP`).
+    def load_checkpoint(path: str, cfg: Optional[PFNConfig] = None, strict: bool = True) -> "PFNWeights":
+        """Load a `tabpfn-v2-regressor.ckpt` / `tabpfn-v2-classifier.ckpt` (blind mapping, see `_CKPT_KEYMAP`).
 
         Upstream stores attention weights as `_w_qkv[3, nhead, d_k, E]` and
         `_w_out[nhead, d_v, E]`; they are flattened to our `[3E, E]` / `[E, E]`
-        (out-projection transposed to `[E_out, E_in]`)."""
+        (out-projection transposed to `[E_out, E_in]`).
+
+        The mapping could not be validated offline (no checkpoint, no `tabpfn`), so it refuses to guess: a missing
+        key raises, a tensor whose element count does not match the target shape raises, and with `strict` (default)
+        any state_dict entry the mapping did NOT consume raises too, listing the leftovers - a silently ignored
+        tensor would mean a silently wrong posterior.  `tests/test_checkpoint_gated.py` compares the loaded model
+        with upstream's own forward whenever a checkpoint and the `tabpfn` package are present."""
         cfg = cfg or PFNConfig()
         ck = torch.load(path, map_location="cpu", weights_only=False)
         sd = ck.get("state_dict", ck)
         km = PFNWeights._CKPT_KEYMAP
-        E, L = cfg.emsize, cfg.nlayers
+        E, L, H, B = cfg.emsize, cfg.nlayers, cfg.nhid, cfg.num_buckets
+        used = set()
 
-        def get(key, l=None):
+        def get(key, l=None, numel=None):
             k = km[key].format(l=l)
             for cand in (k, "model." + k):
                 if cand in sd:
-                    return sd[cand].float()
+                    used.add(cand)
+                    w = sd[cand].float()
+                    if numel is not None and w.numel() != numel:
+                        raise ValueError(f"checkpoint tensor {cand!r} has {w.numel()} elements, expected {numel} "
+                                         f"(shape {tuple(w.shape)}); wrong architecture config or key map")
+                    return w
             raise KeyError(f"checkpoint key {k!r} not found; fix PFNWeights._CKPT_KEYMAP")
 
         def qkv(prefix, l):
             try:
-                w = get(prefix + "_wqkv", l)  # [3, H, dk, E]
+                w = get(prefix + "_wqkv", l, 3 * E * E)  # [3, H, dk, E]
                 return w.reshape(3 * E, E)
             except KeyError:
-                q = get(prefix + "_wq", l).reshape(E, E)
-                kv = get(prefix + "_wkv", l).reshape(2 * E, E)
+                q = get(prefix + "_wq", l, E * E).reshape(E, E)
+                kv = get(prefix + "_wkv", l, 2 * E * E).reshape(2 * E, E)
                 return torch.cat([q, kv], 0)
 
         def wo(prefix, l):
-            w = get(prefix + "_wo", l)  # [H, dv, E_out]
+            w = get(prefix + "_wo", l, E * E)  # [H, dv, E_out]
             return w.reshape(E, E).T.contiguous()
 
         t: Dict[str, torch.Tensor] = {}
-        t["enc_x_w"] = get("enc_x_w")
-        t["enc_y_w"] = get("enc_y_w")
-        t["enc_y_b"] = get("enc_y_b")
+        t["enc_x_w"] = get("enc_x_w", numel=4 * E).reshape(E, 4)
+        t["enc_y_w"] = get("enc_y_w", numel=2 * E).reshape(E, 2)
+        t["enc_y_b"] = get("enc_y_b", numel=E)
+        # upstream draws the subspace embedding inputs from a CPU generator seeded with the model seed at every forward
         g = torch.Generator(device="cpu").manual_seed(cfg.seed)
         pos_raw = torch.randn(cfg.max_groups, cfg.pos_dim, generator=g)
-        t["pos_emb"] = (pos_raw @ get("pos_w").T + get("pos_b")).contiguous()
+        t["pos_emb"] = (pos_raw @ get("pos_w", numel=E * cfg.pos_dim).reshape(E, cfg.pos_dim).T + get("pos_b", numel=E)).contiguous()
         t["feat_wqkv"] = torch.stack([qkv("feat", l) for l in range(L)])
         t["feat_wo"] = torch.stack([wo("feat", l) for l in range(L)])
         t["item_wqkv"] = torch.stack([qkv("item", l) for l in range(L)])
         t["item_wo"] = torch.stack([wo("item", l) for l in range(L)])
-        t["mlp_w1"] = torch.stack([get("mlp_w1", l) for l in range(L)])
-        t["mlp_w2"] = torch.stack([get("mlp_w2", l) for l in range(L)])
-        for k in ("dec_w1", "dec_b1", "dec_w2", "dec_b2", "borders"):
-            t[k] = get(k)
+        t["mlp_w1"] = torch.stack([get("mlp_w1", l, H * E).reshape(H, E) for l in range(L)])
+        t["mlp_w2"] = torch.stack([get("mlp_w2", l, E * H).reshape(E, H) for l in range(L)])
+        t["dec_w1"] = get("dec_w1", numel=H * E).reshape(H, E)
+        t["dec_b1"] = get("dec_b1", numel=H)
+        t["dec_w2"] = get("dec_w2", numel=B * H).reshape(B, H)
+        t["dec_b2"] = get("dec_b2", numel=B)
+        try:
+            t["borders"] = get("borders", numel=B + 1)
+        except KeyError:
+            if B >= 100:
+                raise  # a regressor checkpoint must carry its bucket borders
+            t["borders"] = default_borders(B)  # classifier: unused
+        leftover = sorted(k for k in sd if k not in used and torch.is_tensor(sd[k]) and sd[k].numel() > 1)
+        if strict and leftover:
+            raise ValueError(f"checkpoint {path!r}: {len(leftover)} tensors were not consumed by the key map "
+                             f"(first: {leftover[:8]}); refusing to run a partially loaded model - extend "
+                             f"PFNWeights._CKPT_KEYMAP or pass strict=False after checking them")
         return PFNWeights(cfg, {k: v.contiguous() for k, v in t.items()})
 
     @staticmethod
-    def default(cfg: Optional[PFNConfig] = None) -> "PFNWeights":
-        """Real checkpoint if `NPE_PFN_B200_CKPT` points at one, else seeded random init."""
-        path = os.environ.get("NPE_PFN_B200_CKPT", "")
-        if path and os.path.exists(path):
+    def default(cfg: Optional[PFNConfig] = None, env: str = "NPE_PFN_B200_CKPT",
+                allow_random_init: Optional[bool] = None) -> "PFNWeights":
+        """Weights for an estimator constructed without explicit `weights`.
+
+        `$NPE_PFN_B200_CKPT` (`$NPE_PFN_B200_CLASSIFIER_CKPT` for the classifier) must point at a TabPFNv2 checkpoint.
+        Nothing else is guessed: a path that does not exist raises, and with no checkpoint configured this raises as
+        well unless random initialisation was asked for explicitly (`allow_random_init=True`, or
+        `NPE_PFN_B200_ALLOW_RANDOM_INIT=1` as the tests and bench.py set it) - an untrained network returns
+        well-formed but meaningless posteriors, which must never happen silently."""
+        path = os.environ.get(env, "")
+        if path:
+            if not os.path.exists(path):
+                raise FileNotFoundError(f"${env} = {path!r} does not exist")
             return PFNWeights.load_checkpoint(path, cfg)
+        if allow_random_init is None:
+            allow_random_init = os.environ.get("NPE_PFN_B200_ALLOW_RANDOM_INIT", "") not in ("", "0")
+        if not allow_random_init:
+            raise RuntimeError(
+                f"no TabPFNv2 checkpoint configured: set ${env} to the checkpoint file, pass `weights=` explicitly "
+                "(regressor_init_kwargs / classifier_init_kwargs), or opt in to an UNTRAINED seeded random "
+                "initialisation with NPE_PFN_B200_ALLOW_RANDOM_INIT=1 (benchmarks and tests only)")
+        import warnings
+        warnings.warn(f"${env} is not set: using a seeded RANDOM initialisation of the TabPFNv2 architecture "
+                      "(NPE_PFN_B200_ALLOW_RANDOM_INIT); posteriors are meaningless", RuntimeWarning, stacklevel=2)
         return PFNWeights.random_init(cfg)
 
 

@@ -33,12 +33,14 @@ def default_weights() -> PFNWeights:
 
 
 def y_standardise(y: torch.Tensor):
-    """(y_mean, y_std) as fp32 from fp64 accumulation; unbiased std; std 0 -> 1."""
+    """(y_mean, y_std) as fp32 from fp64 accumulation.  Upstream `TabPFNRegressor.fit` standardises the target with
+    numpy's POPULATION standard deviation plus 1e-20 (`np.std(y) + 1e-20`, SURVEY.md Appendix A.3 [U]); a constant
+    target (std 0, where upstream would divide by 1e-20) keeps unit scale here."""
     yd = y.double()
     mean = yd.mean()
-    std = yd.std(unbiased=True) if y.numel() > 1 else torch.tensor(0.0, dtype=torch.float64)
+    std = yd.std(unbiased=False) if y.numel() > 1 else torch.tensor(0.0, dtype=torch.float64)
     mean32 = np.float32(mean.item())
-    std32 = np.float32(std.item())
+    std32 = np.float32(std.item() + 1e-20) if std.item() > 0 else np.float32(0.0)
     if not np.isfinite(std32) or std32 == 0:
         std32 = np.float32(1.0)
     yz = (y.float() - torch.tensor(mean32)) / torch.tensor(std32)

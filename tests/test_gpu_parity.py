@@ -34,7 +34,7 @@ def _toy(N, dx, dth, seed):
 def test_library_loaded_and_abi(engine):
     from npe_pfn_b200.engine import ABI_SYMBOLS, load_library
     L = load_library()
-    assert L.pfn_abi_version() == 1
+    assert L.pfn_abi_version() == 2
     for s in ABI_SYMBOLS:
         assert hasattr(L, s)
     assert engine.launch_count >= 1

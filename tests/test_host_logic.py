@@ -22,7 +22,7 @@ def test_abi_symbols_match_header():
     L = load_library()
     for s in declared:
         assert hasattr(L, s), s
-    assert L.pfn_abi_version() == 1
+    assert L.pfn_abi_version() == 2
 
 
 def test_no_cpu_fallback():
@@ -32,8 +32,19 @@ def test_no_cpu_fallback():
     from npe_pfn_b200.engine import Engine
     with pytest.raises(RuntimeError):
         Engine()
+    # a posterior object can be constructed and filled anywhere (like the reference's, and so it can be unpickled on a
+    # login node); anything that computes needs the engine and fails loudly without a CUDA device - no CPU path
+    prior = torch.distributions.MultivariateNormal(torch.zeros(2), torch.eye(2))
+    post = NPE_PFN_Core(prior=prior, regressor_init_kwargs={"n_estimators": 1})
+    post.append_simulations(torch.randn(8, 2), torch.randn(8, 3))
     with pytest.raises(RuntimeError):
-        NPE_PFN_Core()
+        post.engine
+    with pytest.raises(RuntimeError):
+        post.sample((4,), torch.randn(1, 3))
+    with pytest.raises(RuntimeError):
+        post.log_prob(torch.randn(4, 2), torch.randn(1, 3))
+    with pytest.raises(RuntimeError):
+        post.sample_batched(torch.randn(2, 3), (4,))
 
 
 def test_product_does_not_import_oracle():
