@@ -128,11 +128,12 @@ int pfn_filter_context(pfn_ctx* ctx, const float* x_train, int64_t ld, int64_t N
 int pfn_slot_info(pfn_ctx* ctx, int slot, int64_t* N, int32_t* F, int32_t* T, int64_t* kv_bytes);
 /* number of kernels this library launched since creation (bench.py's gpu_launches) */
 int64_t pfn_launch_count(pfn_ctx* ctx);
-/* per-class device time of the launches recorded while "time_kernels" was on (host arrays of 5:
+/* per-class device time of the launches recorded while "time_kernels" was on (host arrays of n_classes >= 9:
  * 0 = item attention of test rows, 1 = item attention of context rows, 2 = projection GEMMs, 3 = other,
- * 4 = fused MLP sub-layer):
- * summed milliseconds, launch counts and algorithmic FLOPs.  Synchronises the device. */
-int pfn_kernel_times(pfn_ctx* ctx, double* ms, int64_t* counts, double* flops, int reset);
+ * 4 = fused MLP sub-layer, 5 = bar-distribution head, 6 = cell encoder, 7 = K/V cache writer, 8 = support check +
+ * compaction): summed milliseconds, launch counts, algorithmic FLOPs and (HBM-bound classes) algorithmic bytes.
+ * Synchronises the device. */
+int pfn_kernel_times(pfn_ctx* ctx, double* ms, int64_t* counts, double* flops, double* bytes, int n_classes, int reset);
 /* debug / parity: copy a slot's derived quantities to caller device buffers (any may be NULL):
  * stats[3 * 2G] = mean | std | group scale (first G), y_stats[2] = mean, std, borders[num_buckets+1],
  * kv[L][T][N][64] bf16 (K 0..31 | V 32..63). */

@@ -101,12 +101,14 @@ struct pfn_ctx {
     int num_sms = 148;
     // optional per-class kernel timing (bench.py roofline): CUDA events around each launch on its stream
     int time_kernels = 0;
-    struct Timed { cudaEvent_t a, b; int cls; double flops; };
+    struct Timed { cudaEvent_t a, b; int cls; double flops, bytes; };
     std::vector<Timed> timed;
     std::vector<cudaEvent_t> ev_pool;
 };
 
-enum KernelClass { KC_ATTN_TEST = 0, KC_ATTN_CTX = 1, KC_GEMM = 2, KC_OTHER = 3, KC_MLP = 4, KC_COUNT = 5 };
+// classes 5..7 are the HBM-bound kernels north_star wants reported against the measured copy bandwidth
+enum KernelClass { KC_ATTN_TEST = 0, KC_ATTN_CTX = 1, KC_GEMM = 2, KC_OTHER = 3, KC_MLP = 4, KC_HEAD = 5, KC_ENCODE = 6, KC_KVCACHE = 7,
+                   KC_COMPACT = 8, KC_COUNT = 9 };
 
 namespace {
 
@@ -178,8 +180,8 @@ cudaEvent_t take_event(pfn_ctx* c) {
 }
 struct TimeScope {  // records an event pair around the launches issued inside its lifetime
     pfn_ctx* c; cudaStream_t st; pfn_ctx::Timed t; bool on;
-    TimeScope(pfn_ctx* c_, cudaStream_t st_, int cls, double flops) : c(c_), st(st_), on(c_->time_kernels != 0) {
-        if (on) { t.a = take_event(c); t.b = take_event(c); t.cls = cls; t.flops = flops; cudaEventRecord(t.a, st); }
+    TimeScope(pfn_ctx* c_, cudaStream_t st_, int cls, double flops, double bytes = 0.0) : c(c_), st(st_), on(c_->time_kernels != 0) {
+        if (on) { t.a = take_event(c); t.b = take_event(c); t.cls = cls; t.flops = flops; t.bytes = bytes; cudaEventRecord(t.a, st); }
     }
     ~TimeScope() { if (on) { cudaEventRecord(t.b, st); c->timed.push_back(t); } }
 };
@@ -224,10 +226,14 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
     const bf16* wb = c->wb;
     const Offsets& o = c->off;
 
-    encode_kernel<<<(unsigned)ceil_div(R, ENC_ROWS), kE, 0, st>>>(X, ldx, s.F, G, y, R, s.enc, wf + o.enc_x_w,
-                                                                 wf + o.enc_y_w, wf + o.enc_y_b, wf + o.pos_emb, c->xf,
-                                                                 c->xb);
-    PFN_LAUNCH_OK(c);
+    {
+        // algorithmic bytes: F raw features (+ y) in, T tokens of 192 (fp32 + bf16 copy) out per row
+        TimeScope ts(c, st, KC_ENCODE, 0.0, (double)R * (4.0 * (s.F + (ctx_rows ? 1 : 0)) + 6.0 * T * kE));
+        encode_kernel<<<(unsigned)ceil_div(R, ENC_ROWS), kE, 0, st>>>(X, ldx, s.F, G, y, R, s.enc, wf + o.enc_x_w,
+                                                                     wf + o.enc_y_w, wf + o.enc_y_b, wf + o.pos_emb, c->xf,
+                                                                     c->xb);
+        PFN_LAUNCH_OK(c);
+    }
 
     const size_t fa_smem = (size_t)FA_WARPS * 2 * T * 33 * sizeof(float);
     if (fa_smem > 48 * 1024)
@@ -272,8 +278,11 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
             g.N = 3 * kE; g.Cb = c->qkv + t0 * 3 * kE; g.ldcb = 3 * kE;
             if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
             bf16* cache_l = s.kv + (size_t)l * T * s.N * kKvRow;
-            kv_cache_kernel<<<(unsigned)ceil_div(ntok * 8, 256), 256, 0, st>>>(c->qkv + t0 * 3 * kE, nr, T, r0, s.N, cache_l);
-            PFN_LAUNCH_OK(c);
+            {
+                TimeScope ts(c, st, KC_KVCACHE, 0.0, (double)ntok * 2.0 * kKvRow * sizeof(bf16));  // 128 B read + 128 B written per token
+                kv_cache_kernel<<<(unsigned)ceil_div(ntok * 8, 256), 256, 0, st>>>(c->qkv + t0 * 3 * kE, nr, T, r0, s.N, cache_l);
+                PFN_LAUNCH_OK(c);
+            }
         } else {
             g.N = kE; g.Cb = c->qkv + off; g.ldcb = ld;  // Q rows of the projection only
             if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
@@ -361,6 +370,9 @@ int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
         if (sample) PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
+    // algorithmic bytes: every distinct logits row once (20 000 B) + the row's scalar inputs / outputs
+    const double rows_read = h.ld_logits == 0 ? 1.0 : (double)ceil_div(h.M, h.group);
+    TimeScope ts(c, st, KC_HEAD, 0.0, rows_read * h.B * 4.0 + (double)h.M * 12.0);
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(h.M, HEAD_WARPS), 148 * 8);
     if (sample) head_kernel<true><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
     else head_kernel<false><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
@@ -733,15 +745,16 @@ int pfn_slot_info(pfn_ctx* c, int slot, int64_t* N, int32_t* F, int32_t* T, int6
 
 int64_t pfn_launch_count(pfn_ctx* c) { return c ? c->launches : 0; }
 
-int pfn_kernel_times(pfn_ctx* c, double* ms, int64_t* counts, double* flops, int reset) {
-    PFN_REQUIRE(c && ms && counts && flops, "null argument");
+int pfn_kernel_times(pfn_ctx* c, double* ms, int64_t* counts, double* flops, double* bytes, int n_classes, int reset) {
+    PFN_REQUIRE(c && ms && counts && flops && bytes, "null argument");
+    PFN_REQUIRE(n_classes >= KC_COUNT, "output arrays are shorter than the number of kernel classes");
     PFN_CUDA_OK(cudaSetDevice(c->device));
     PFN_CUDA_OK(cudaDeviceSynchronize());
-    for (int k = 0; k < KC_COUNT; ++k) { ms[k] = 0.0; counts[k] = 0; flops[k] = 0.0; }
+    for (int k = 0; k < n_classes; ++k) { ms[k] = 0.0; counts[k] = 0; flops[k] = 0.0; bytes[k] = 0.0; }
     for (auto& t : c->timed) {
         float e = 0.f;
         PFN_CUDA_OK(cudaEventElapsedTime(&e, t.a, t.b));
-        ms[t.cls] += e; counts[t.cls] += 1; flops[t.cls] += t.flops;
+        ms[t.cls] += e; counts[t.cls] += 1; flops[t.cls] += t.flops; bytes[t.cls] += t.bytes;
     }
     if (reset) {
         for (auto& t : c->timed) { c->ev_pool.push_back(t.a); c->ev_pool.push_back(t.b); }

@@ -552,83 +552,146 @@ __global__ void __launch_bounds__(HEAD_WARPS * 32) head_kernel(HeadArgs a) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// support check + ordered stream compaction (accept_reject_sampler.py:54-62)
+// support check + ordered stream compaction (accept_reject_sampler.py:54-62, support_posterior.py:152-156)
+//
+// ONE kernel, one pass: every thread evaluates the accept predicate of its rows once, a warp ballot + popcount gives
+// the position inside the warp, a shared-memory scan the position inside the block, and a decoupled look-back over the
+// per-block aggregates the position in the whole stream (blocks take their index from an atomic ticket, so a block
+// only ever waits for blocks that are already running).  Accepted rows are APPENDED to the output at a device-resident
+// cursor, in proposal order, and the cursor / proposal counters are advanced by the last block - a rejection loop can
+// enqueue round after round without the host ever reading a count (north_star 4).
 // ---------------------------------------------------------------------------------------------
-constexpr int CP_THREADS = 256;
+constexpr int CP_THREADS = 256, CP_ITEMS = 4, CP_TILE = CP_THREADS * CP_ITEMS;
 
-__device__ __forceinline__ bool row_accepted(const float* __restrict__ theta, int64_t ld, int64_t r, int dim,
-                                             const float* __restrict__ lo, const float* __restrict__ hi,
-                                             const uint8_t* __restrict__ mask) {
-    bool ok = mask ? mask[r] != 0 : true;
-    for (int j = 0; j < dim; ++j) {
-        const float v = theta[r * ld + j];
+struct CompactArgs {
+    const float* theta; int64_t ld; int64_t M; int dim;
+    const float* lo; const float* hi;       // box (any may be null)
+    const uint8_t* mask;                    // optional precomputed predicate
+    const float* score; const float* thr;   // optional: accept only rows with score[r] > *thr (device scalar)
+    const float* logp;                      // optional per-row payload carried along with accepted rows
+    int64_t* out_idx; float* out_rows; float* out_logp;
+    int64_t out_ld;                         // row stride of out_rows (floats)
+    int64_t capacity;                       // rows that fit into out_* (rows past it are counted, not written)
+    int64_t* cursor;                        // device: [0] accepted so far (append position), [1] proposed so far
+    int64_t* out_count;                     // optional: number accepted in THIS call
+    unsigned long long* tile_state;         // [nblocks] (flag << 62 | value), zeroed before the launch
+    unsigned int* ticket;                   // zeroed before the launch
+};
+
+__device__ __forceinline__ bool row_accepted(const CompactArgs& a, int64_t r) {
+    bool ok = a.mask ? a.mask[r] != 0 : true;
+    for (int j = 0; j < a.dim; ++j) {
+        const float v = a.theta[r * a.ld + j];
         ok = ok && isfinite(v);
-        if (lo) ok = ok && (v >= lo[j]);
-        if (hi) ok = ok && (v <= hi[j]);
+        if (a.lo) ok = ok && (v >= a.lo[j]);
+        if (a.hi) ok = ok && (v <= a.hi[j]);
     }
+    if (a.score) ok = ok && (a.score[r] > *a.thr);
     return ok;
 }
 
-__global__ void __launch_bounds__(CP_THREADS) compact_count_kernel(const float* theta, int64_t ld, int64_t M, int dim,
-                                                                   const float* lo, const float* hi,
-                                                                   const uint8_t* mask, int32_t* block_counts) {
-    __shared__ int wc[CP_THREADS / 32];
-    const int64_t r = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x;
-    const bool ok = r < M && row_accepted(theta, ld, r, dim, lo, hi, mask);
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    if ((threadIdx.x & 31) == 0) wc[threadIdx.x >> 5] = __popc(bal);
+__global__ void __launch_bounds__(CP_THREADS) compact_append_kernel(const CompactArgs a) {
+    __shared__ int wsum[CP_THREADS / 32];
+    __shared__ unsigned int s_tile;
+    __shared__ long long s_prefix;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_tile = atomicAdd(a.ticket, 1u);
+    __syncthreads();
+    const unsigned int tile = s_tile;
+    const unsigned int ntiles = gridDim.x;
+    // thread t owns CP_ITEMS CONSECUTIVE rows: order inside the tile = (thread, item)
+    const int64_t r0 = (int64_t)tile * CP_TILE + (int64_t)threadIdx.x * CP_ITEMS;
+    bool ok[CP_ITEMS];
+    int mine = 0;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i) {
+        ok[i] = (r0 + i < a.M) && row_accepted(a, r0 + i);
+        mine += ok[i];
+    }
+    // exclusive scan of `mine` over the block: warp shuffle scan + scan of the warp sums
+    int inc = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) wsum[warp] = inc;
+    __syncthreads();
+    int before = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < CP_THREADS / 32; ++w) {
+        if (w < warp) before += wsum[w];
+        total += wsum[w];
+    }
+    const int excl = before + inc - mine;
+    // decoupled look-back: publish the aggregate, then sum the predecessors' states
+    if (threadIdx.x == 0) {
+        long long prefix = 0;
+        if (tile == 0) {
+            atomicExch(a.tile_state + 0, (2ull << 62) | (unsigned long long)total);
+        } else {
+            atomicExch(a.tile_state + tile, (1ull << 62) | (unsigned long long)total);
+            for (long long p = (long long)tile - 1; p >= 0; --p) {
+                unsigned long long st;
+                do { st = atomicAdd(a.tile_state + p, 0ull); } while ((st >> 62) == 0ull);
+                prefix += (long long)(st & ((1ull << 62) - 1ull));
+                if ((st >> 62) == 2ull) break;
+            }
+            atomicExch(a.tile_state + tile, (2ull << 62) | (unsigned long long)(prefix + total));
+        }
+        s_prefix = prefix;
+    }
+    __syncthreads();
+    const int64_t base = a.cursor ? a.cursor[0] : 0;
+    int64_t pos = base + s_prefix + excl;
+#pragma unroll
+    for (int i = 0; i < CP_ITEMS; ++i) {
+        if (ok[i]) {
+            if (pos < a.capacity) {
+                const int64_t r = r0 + i;
+                if (a.out_idx) a.out_idx[pos] = r;
+                if (a.out_rows)
+                    for (int j = 0; j < a.dim; ++j) a.out_rows[pos * a.out_ld + j] = a.theta[r * a.ld + j];
+                if (a.out_logp && a.logp) a.out_logp[pos] = a.logp[r];
+            }
+            ++pos;
+        }
+    }
+    // the last tile in TICKET order knows the grand total; it may only advance the cursor after every block has read
+    // it, so the cursor update is done by whichever block finishes LAST (second ticket counter)
+    __shared__ bool s_last;
     __syncthreads();
     if (threadIdx.x == 0) {
-        int s = 0;
-        for (int w = 0; w < CP_THREADS / 32; ++w) s += wc[w];
-        block_counts[blockIdx.x] = s;
+        __threadfence();
+        s_last = atomicAdd(a.ticket + 1, 1u) == ntiles - 1;
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x == 0) {
+        unsigned long long st;
+        do { st = atomicAdd(a.tile_state + (ntiles - 1), 0ull); } while ((st >> 62) != 2ull);
+        const long long grand = (long long)(st & ((1ull << 62) - 1ull));
+        if (a.out_count) *a.out_count = grand;
+        if (a.cursor) { a.cursor[0] = base + grand; a.cursor[1] += a.M; }
     }
 }
 
-// exclusive scan of the block counts (single block; nblocks <= a few 10^4)
-__global__ void __launch_bounds__(1024) compact_scan_kernel(const int32_t* block_counts, int64_t nblocks,
-                                                            int64_t* block_offsets, int64_t* out_count) {
-    __shared__ long long sh[1024];
-    __shared__ long long carry;
-    if (threadIdx.x == 0) carry = 0;
-    __syncthreads();
-    for (int64_t base = 0; base < nblocks; base += 1024) {
-        const int64_t i = base + threadIdx.x;
-        const long long v = i < nblocks ? block_counts[i] : 0;
-        sh[threadIdx.x] = v;
-        __syncthreads();
-        for (int o = 1; o < 1024; o <<= 1) {
-            long long t = threadIdx.x >= o ? sh[threadIdx.x - o] : 0;
-            __syncthreads();
-            sh[threadIdx.x] += t;
-            __syncthreads();
+// uniform proposals on a box (`BoxUniform.sample`, support_posterior.py:137 / :305-309): out[r, j] = lo[j] + u (hi[j] - lo[j]),
+// u from Philox4x32-10 keyed by (seed; counter = (row0 + r, j / 4)), 23-bit mantissa, strictly inside (0, 1)
+__global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, int64_t M, int dim, uint64_t seed,
+                                   uint64_t row0, float* __restrict__ out, int64_t ld) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= M) return;
+    for (int j0 = 0; j0 < dim; j0 += 4) {
+        uint32_t c[4];
+        philox4x32_10(seed, row0 + (uint64_t)r, 0x5EED0000ull + (uint64_t)(j0 >> 2), c);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int j = j0 + k;
+            if (j < dim) {
+                const float u = ((float)(c[k] >> 9) + 0.5f) * 0x1.0p-23f;
+                out[r * ld + j] = fmaf(u, hi[j] - lo[j], lo[j]);
+            }
         }
-        if (i < nblocks) block_offsets[i] = carry + sh[threadIdx.x] - v;
-        __syncthreads();
-        if (threadIdx.x == 0) carry += sh[1023];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *out_count = carry;
-}
-
-__global__ void __launch_bounds__(CP_THREADS) compact_scatter_kernel(const float* theta, int64_t ld, int64_t M, int dim,
-                                                                     const float* lo, const float* hi,
-                                                                     const uint8_t* mask, const int64_t* block_offsets,
-                                                                     int64_t* out_idx, float* out_rows) {
-    __shared__ int wc[CP_THREADS / 32];
-    const int64_t r = (int64_t)blockIdx.x * CP_THREADS + threadIdx.x;
-    const bool ok = r < M && row_accepted(theta, ld, r, dim, lo, hi, mask);
-    const unsigned bal = __ballot_sync(0xffffffffu, ok);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    if (lane == 0) wc[warp] = __popc(bal);
-    __syncthreads();
-    int before = 0;
-    for (int w = 0; w < warp; ++w) before += wc[w];
-    if (ok) {
-        const int64_t pos = block_offsets[blockIdx.x] + before + __popc(bal & ((1u << lane) - 1u));
-        if (out_idx) out_idx[pos] = r;
-        if (out_rows)
-            for (int j = 0; j < dim; ++j) out_rows[pos * dim + j] = theta[r * ld + j];
     }
 }
 

@@ -93,7 +93,8 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_launch_count.restype = i64
     L.pfn_launch_count.argtypes = [vp]
     L.pfn_kernel_times.restype = c.c_int
-    L.pfn_kernel_times.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i64), c.POINTER(c.c_double), c.c_int]
+    L.pfn_kernel_times.argtypes = [vp, c.POINTER(c.c_double), c.POINTER(i64), c.POINTER(c.c_double), c.POINTER(c.c_double), c.c_int,
+                                   c.c_int]
     L.pfn_slot_export.restype = c.c_int
     L.pfn_slot_export.argtypes = [vp, c.c_int, vp, vp, vp, vp, vp]
     L.pfn_slot_state.restype = c.c_int
@@ -286,12 +287,16 @@ class Engine:
         self._check(self.lib.pfn_attn_debug_counts(self._h, out))
         return tuple(int(v) for v in out)
 
-    def kernel_times(self, reset: bool = True):
-        """{class: (ms, launches, flops)} of the launches recorded while option "time_kernels" was on."""
-        ms, cnt, fl = (c.c_double * 5)(), (c.c_int64 * 5)(), (c.c_double * 5)()
-        self._check(self.lib.pfn_kernel_times(self._h, ms, cnt, fl, int(reset)))
-        names = ["attn_test", "attn_ctx", "gemm", "other", "mlp"]
-        return {n: (ms[i], cnt[i], fl[i]) for i, n in enumerate(names)}
+    KERNEL_CLASSES = ["attn_test", "attn_ctx", "gemm", "other", "mlp", "head", "encode", "kv_cache", "compact"]
+
+    def kernel_times(self, reset: bool = True, with_bytes: bool = False):
+        """{class: (ms, launches, flops[, bytes])} of the launches recorded while option "time_kernels" was on."""
+        n = len(self.KERNEL_CLASSES)
+        ms, cnt, fl, by = (c.c_double * n)(), (c.c_int64 * n)(), (c.c_double * n)(), (c.c_double * n)()
+        self._check(self.lib.pfn_kernel_times(self._h, ms, cnt, fl, by, n, int(reset)))
+        if with_bytes:
+            return {k: (ms[i], cnt[i], fl[i], by[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
+        return {k: (ms[i], cnt[i], fl[i]) for i, k in enumerate(self.KERNEL_CLASSES)}
 
     def filter_context(self, x_train: torch.Tensor, obs: torch.Tensor, k: int, want_dist: bool = False):
         """Indices (int64, CUDA) of the k simulations nearest to `obs` in z-scored x, ascending distance."""

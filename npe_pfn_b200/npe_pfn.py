@@ -70,6 +70,10 @@ class NPE_PFN_Core:
         self._prior_bounds = "unset"
         #: extra Philox row offset (distinct per rank when draws are sharded over GPUs)
         self.rank_row_offset = 0
+        #: sample_batched, rounds 2..10: False = draw only for observations that are still short (same result
+        #: distribution, less work); True = the reference's literal schedule, which re-draws for every observation and
+        #: discards (npe_pfn.py:375-383) - used to pin the mirror against the reference draw for draw
+        self.redraw_all_observations = False
         #: opt-in for multi-GPU jobs whose ranks hold the SAME simulations and call sample / log_prob together:
         #: split the per-dimension prefills over the ranks and exchange the slots over NCCL (`prefill_sharded`)
         self.shard_prefill = False
@@ -299,9 +303,14 @@ class NPE_PFN_Core:
         return theta, lp
 
     def _sample_batched(self, x: Tensor, num_samples_per_obs: int, with_log_prob: bool = False, eps: float = 1e-15,
-                        return_device: bool = False, seed: Optional[int] = None):
+                        return_device: bool = False, seed: Optional[int] = None, uniforms: Optional[Tensor] = None,
+                        return_bins: bool = False):
         """All observations against one shared, unfiltered context (npe_pfn.py:171-251):
-        -> theta [num_obs, n, dim_theta], log_probs [num_obs, n] | None."""
+        -> theta [num_obs, n, dim_theta], log_probs [num_obs, n] | None.
+
+        Test row r = o * n + i is draw i of observation o (`repeat_interleave`, npe_pfn.py:199).  Dimension 0 sees n
+        identical rows per observation, so its logits are computed once per observation and ONE head launch draws
+        n samples from each logits row (`group = n`).  `uniforms[num_obs * n, dim_theta]` may be injected."""
         num_obs = x.shape[0]
         n = int(num_samples_per_obs)
         ctx = self._prepare_context(x, use_filter=False)
@@ -311,30 +320,34 @@ class NPE_PFN_Core:
         xd = x.to(dev, torch.float32)
         M = num_obs * n
         buf = torch.empty(M, dx + dth, dtype=torch.float32, device=dev)
-        buf[:, :dx] = xd.repeat_interleave(n, dim=0)
+        buf.view(num_obs, n, dx + dth)[:, :, :dx] = xd[:, None, :]
         lp = torch.zeros(M, dtype=torch.float32, device=dev) if with_log_prob else None
-        if seed is None:
+        bins = torch.empty(dth, M, dtype=torch.int32, device=dev) if return_bins else None
+        if uniforms is not None:
+            uniforms = uniforms.to(dev, torch.float32).t().contiguous()  # [dth, M]
+        elif seed is None:
             seed = draw_seed()
         row0 = self.rank_row_offset
         for d in range(dth):
             slot = self._ensure_slot(ctx, d)
-            if d == 0 and n > 1:
-                # rows of one observation share their features: num_obs forward rows, n draws from each
-                logits = self._logits(slot, xd)
-                for o in range(num_obs):
-                    eng.head_sample(slot, logits[o:o + 1], M=n, seed=seed, row0=row0 + o * n, offset=0,
-                                    out_theta=buf[o * n:(o + 1) * n, dx], ld_theta=buf.stride(0),
-                                    out_logp=lp[o * n:(o + 1) * n] if lp is not None else None, eps=eps,
-                                    accumulate=True)
+            u_d = uniforms[d] if uniforms is not None else None
+            b_d = bins[d] if bins is not None else None
+            if d == 0 and n > 1 and M > 0:
+                logits = self._logits(slot, xd)  # [num_obs, B]
+                eng.head_sample(slot, logits, M=M, group=n, uniforms=u_d, seed=seed or 0, row0=row0, offset=0,
+                                out_theta=buf[:, dx], ld_theta=buf.stride(0), out_logp=lp, eps=eps, accumulate=True,
+                                bins=b_d)
             else:
-                self._sample_step(slot, buf, dx + d, seed=seed, row0=row0, offset=d, out_logp=lp, eps=eps,
-                                  accumulate=True)
+                self._sample_step(slot, buf, dx + d, uniforms=u_d, seed=seed or 0, row0=row0, offset=d, out_logp=lp,
+                                  eps=eps, accumulate=True, bins=b_d)
         theta = buf[:, dx:].reshape(num_obs, n, dth)
         if lp is not None:
             lp = lp.reshape(num_obs, n)
         if not return_device:
             theta = theta.cpu()
             lp = lp.cpu() if lp is not None else None
+        if return_bins:
+            return theta, lp, bins.t().reshape(num_obs, n, dth)
         return theta, lp
 
     def _autoregressive_log_prob(self, theta: Tensor, x: Tensor = None, repeat_x: bool = True, eps: float = 1e-15,
@@ -428,28 +441,33 @@ class NPE_PFN_Core:
             samples, log_probs = self._sample_batched(x, num_samples, with_log_prob=with_log_prob, eps=eps)
             return (samples, log_probs) if with_log_prob else samples
 
+        if self._bounds() == (None, None):
+            # support = all of R^d: every draw is valid, so "the first num_samples valid draws of each observation"
+            # are simply num_samples draws - no oversampling, no second round
+            samples, log_probs = self._sample_batched(x, num_samples, with_log_prob=with_log_prob, eps=eps)
+            return (samples, log_probs) if with_log_prob else samples
+
         num_to_sample = int(num_samples * oversample_factor)
-        dev = self.engine.device
-        dth = self._theta_train.shape[1]
-        out = torch.empty(num_obs, num_samples, dth, dtype=torch.float32, device=dev)
-        out_lp = torch.empty(num_obs, num_samples, dtype=torch.float32, device=dev) if with_log_prob else None
-        filled = torch.zeros(num_obs, dtype=torch.long, device=dev)
-        obs_index = torch.arange(num_obs, device=dev)[:, None]
+        out = out_lp = filled = None
         max_iter = 10
         for _iteration in range(max_iter):
-            if bool((filled >= num_samples).all()):
+            # observations that still need draws (the reference re-draws for all of them and discards, :380-383)
+            todo = None if filled is None else torch.nonzero(filled < num_samples).flatten()
+            if todo is not None and todo.numel() == 0:
                 break
-            raw, raw_lp = self._sample_batched(x, num_to_sample, with_log_prob=with_log_prob, eps=eps,
+            if todo is not None and self.redraw_all_observations:
+                todo = torch.arange(num_obs, device=filled.device)
+            x_round = x if todo is None else x[todo.to(x.device)]
+            raw, raw_lp = self._sample_batched(x_round, num_to_sample, with_log_prob=with_log_prob, eps=eps,
                                                return_device=True)
-            valid = self._within_support_device(raw.reshape(-1, dth)).reshape(num_obs, num_to_sample)
-            rank = torch.cumsum(valid.long(), dim=1)  # 1-based position among this round's valid draws
-            take = valid & (rank <= (num_samples - filled)[:, None])
-            dst = (filled[:, None] + rank - 1).clamp_(0, num_samples - 1)
-            oi = obs_index.expand_as(dst)[take]
-            out[oi, dst[take]] = raw[take]
-            if with_log_prob:
-                out_lp[oi, dst[take]] = raw_lp[take]
-            filled = filled + take.sum(dim=1)
+            if out is None:
+                dev, dth = raw.device, raw.shape[-1]
+                out = torch.empty(num_obs, num_samples, dth, dtype=torch.float32, device=dev)
+                out_lp = torch.empty(num_obs, num_samples, dtype=torch.float32, device=dev) if with_log_prob else None
+                filled = torch.zeros(num_obs, dtype=torch.long, device=dev)
+                todo = torch.arange(num_obs, device=dev)
+            valid = self._within_support_device(raw.reshape(-1, raw.shape[-1])).reshape(raw.shape[0], num_to_sample)
+            take_first_n(raw, raw_lp, valid, todo, out, out_lp, filled, num_samples)
         if not bool((filled >= num_samples).all()):
             raise RuntimeError("sample_batched: some observations have fewer than num_samples in-support draws "
                                "after 10 rounds (the reference fails here when stacking ragged results)")
@@ -529,6 +547,24 @@ class NPE_PFN_Core:
         if hi is not None:
             ok &= (theta <= hi.to(theta.device)).all(dim=-1)
         return ok
+
+
+def take_first_n(raw: Tensor, raw_lp: Optional[Tensor], valid: Tensor, obs_ids: Tensor, out: Tensor,
+                 out_lp: Optional[Tensor], filled: Tensor, num_samples: int) -> None:
+    """Per observation keep the first in-support draws of this round until `num_samples` are collected
+    (npe_pfn.py:380-397: `valid_samples[:n_take]` appended per observation), without a Python loop over observations:
+    the position of a valid draw among its observation's valid draws is a cumulative sum, the rows still wanted are
+    scattered to `out[obs, filled[obs] + position]`.  `raw [k, m, dth]` / `valid [k, m]` hold this round's draws of the
+    observations `obs_ids [k]`; `filled [num_obs]` is updated in place.  Works on any device."""
+    rank = torch.cumsum(valid.long(), dim=1)  # 1-based position among this round's valid draws
+    base = filled[obs_ids]
+    take = valid & (rank <= (num_samples - base)[:, None])
+    dst = (base[:, None] + rank - 1).clamp_(0, num_samples - 1)
+    oi = obs_ids[:, None].expand_as(dst)[take]
+    out[oi, dst[take]] = raw[take]
+    if out_lp is not None:
+        out_lp[oi, dst[take]] = raw_lp[take]
+    filled[obs_ids] = base + take.sum(dim=1)
 
 
 class _SupportCheck:

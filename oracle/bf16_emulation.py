@@ -60,12 +60,22 @@ def _mlp(w, l, x):
     return base._ln(x + h @ r(w.mlp_w2[l]).T, w.cfg.ln_eps)
 
 
-def _item_attn(q, k, v):
-    """q [B, Lq, dh] pre-scaled (log2 domain), k / v [B, Lk, dh], all bf16-valued -> bf16-valued output."""
-    s = q @ k.transpose(-1, -2)
-    m = torch.round(s.max(dim=-1, keepdim=True).values)  # integer reference: P's mantissa is independent of it
-    p = torch.exp2(s - m)
-    return r((r(p) @ v) / p.sum(-1, keepdim=True))
+def _item_attn(q, k, v, max_elems: int = 1 << 27):
+    """q [B, Lq, dh] pre-scaled (log2 domain), k / v [B, Lk, dh] or [Lk, dh], all bf16-valued -> bf16-valued output.
+    Processed in slices of the batch dimension so the score matrix stays below `max_elems` elements."""
+    B, Lq = q.shape[0], q.shape[1]
+    Lk = k.shape[-2]
+    step = max(1, max_elems // max(Lq * Lk, 1))
+    outs = []
+    for b0 in range(0, B, step):
+        qb = q[b0:b0 + step]
+        kb = k[b0:b0 + step] if k.ndim == 3 and k.shape[0] == B else k
+        vb = v[b0:b0 + step] if v.ndim == 3 and v.shape[0] == B else v
+        s = qb @ kb.transpose(-1, -2)
+        m = torch.round(s.max(dim=-1, keepdim=True).values)  # integer reference: P's mantissa is independent of it
+        p = torch.exp2(s - m)
+        outs.append(r((r(p) @ vb) / p.sum(-1, keepdim=True)))
+    return torch.cat(outs, 0)
 
 
 def _wq_scaled(w, l, E):
@@ -116,7 +126,7 @@ def forward_test(w, cache: base.ContextCache, Xt: torch.Tensor, chunk: int = 204
             x = _feature_attn(w, l, x)
             q = r(r(x) @ _wq_scaled(w, l, E).T)
             q = q.reshape(M, T, H, dh).permute(1, 0, 2, 3).reshape(T, M * H, dh)
-            o = _item_attn(q, cache.k0[l], cache.v0[l])
+            o = _item_attn(q, cache.k0[l], cache.v0[l])  # k0 / v0 [T, N, dh]: one key set per column, shared by all heads
             o = o.reshape(T, M, H, dh).permute(1, 0, 2, 3).reshape(M, T, E)
             x = base._ln(x + o @ r(w.item_wo[l]).T, cfg.ln_eps)
             x = _mlp(w, l, x)
@@ -129,8 +139,6 @@ class Bf16EmulatedRegressor:
     """`OracleTabPFNRegressor` with the kernels' roundings (same fit statistics, borders and head)."""
 
     def __init__(self, weights, softmax_temperature: float = 0.9, chunk: int = 2048):
-        from .estimator import OracleTabPFNRegressor
-        self._fp32 = OracleTabPFNRegressor(weights=weights, softmax_temperature=softmax_temperature, chunk=chunk)
         self.w = weights
         self.temperature = float(softmax_temperature)
         self.chunk = chunk
@@ -142,6 +150,27 @@ class Bf16EmulatedRegressor:
         y = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
         self.y_mean, self.y_std, yz = y_standardise(y)
         self.cache = prefill(self.w, X, yz)
+        self.borders_orig = bar_head.renorm_borders(self.w.borders, self.y_mean, self.y_std)
+        return self
+
+    def fit_with_kv(self, X, y, kv: torch.Tensor):
+        """Like `fit`, but the per-layer head-0 K/V of the context rows are GIVEN (`kv [L, T, N, 64]`, K 0..31 | V 32..63,
+        e.g. a slot's cache exported from the device) instead of being recomputed: at 10 000 context rows the emulated
+        context pass would take minutes on the CPU, while the test-row path against a given cache takes seconds."""
+        from . import bar_head
+        from .estimator import y_standardise
+        X = torch.as_tensor(X, dtype=torch.float32)
+        y = torch.as_tensor(y, dtype=torch.float32).reshape(-1)
+        self.y_mean, self.y_std, yz = y_standardise(y)
+        G = (X.shape[1] + 1) // 2
+        cache = base.ContextCache()
+        cache.stats = base.EncoderStats(X, yz, G)
+        cache.T, cache.N = G + 1, X.shape[0]
+        kv = kv.float()
+        assert kv.shape[1:] == (cache.T, cache.N, 64)
+        cache.k0 = [kv[l, :, :, :32].contiguous() for l in range(kv.shape[0])]
+        cache.v0 = [kv[l, :, :, 32:].contiguous() for l in range(kv.shape[0])]
+        self.cache = cache
         self.borders_orig = bar_head.renorm_borders(self.w.borders, self.y_mean, self.y_std)
         return self
 

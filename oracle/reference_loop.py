@@ -7,6 +7,7 @@ the `cpu_baseline` / `--impl reference` leg of bench.py on boxes where
 
   sample_loop   <- NPE_PFN_Core._sample                /root/reference/npe_pfn/npe_pfn.py:111-169
   logprob_loop  <- NPE_PFN_Core._autoregressive_log_prob   /root/reference/npe_pfn/npe_pfn.py:462-524
+  sample_batched_loop <- NPE_PFN_Core._sample_batched       /root/reference/npe_pfn/npe_pfn.py:171-251
 
 Like the reference, every call re-fits the estimator once per dimension.
 `uniforms[M, dim_theta]` may be injected so results are comparable draw by draw.
@@ -61,3 +62,17 @@ def logprob_loop(model: OracleTabPFNRegressor, x_ctx, theta_ctx, x_obs, theta, *
         dlp = torch.where(dlp == float("-inf"), torch.tensor(math.log(eps)), dlp)
         lp += dlp
     return lp
+
+
+def sample_batched_loop(model: OracleTabPFNRegressor, x_ctx, theta_ctx, x_obs, n: int, *, with_log_prob=False,
+                        eps=1e-15, uniforms: Optional[torch.Tensor] = None, return_bins=False):
+    """Many observations against one shared, unfiltered context: test row o * n + i is draw i of observation o
+    (`repeat_interleave`); -> theta [num_obs, n, dim_theta], log_probs [num_obs, n] | None (, bins)."""
+    num_obs = x_obs.shape[0]
+    out = sample_loop(model, x_ctx, theta_ctx, x_obs.repeat_interleave(n, dim=0), num_obs * n,
+                      with_log_prob=with_log_prob, eps=eps, uniforms=uniforms, return_bins=return_bins)
+    theta = out[0].reshape(num_obs, n, -1)
+    lp = out[1].reshape(num_obs, n) if out[1] is not None else None
+    if return_bins:
+        return theta, lp, (out[2].reshape(num_obs, n, -1) if out[2] is not None else None)
+    return theta, lp

@@ -15,7 +15,8 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-LOGIT_ATOL = 0.25      # max |logit_cuda - logit_oracle|; logits have std ~2.6, measured max 0.10-0.14 (r1 on B200)
+LOGIT_ATOL = 0.20      # max |logit_cuda - logit_oracle|; logits have std ~2.6; measured max 0.09-0.131 on B200 (r2), bar = 1.5 x that;
+                       # against the bf16-EMULATING oracle the gap is 0.05 (tests/test_gpu_parity_r2.py::test_bf16_emulated_oracle)
 LOGIT_MEAN_ATOL = 0.035  # measured mean 0.018-0.023
 LOGP_ATOL = 0.08       # per dimension; measured 0.04
 CDF_ATOL = 0.06        # end-to-end shift of the inverse-CDF position in probability mass (buckets / 5000)

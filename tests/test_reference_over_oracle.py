@@ -130,3 +130,141 @@ def test_reference_loops_over_the_ensemble_oracle(ref_pkg, weights):
     assert torch.equal(s_ref, s_me) and torch.allclose(lp_ref, lp_me, atol=1e-6)
     th = torch.randn(5, 2, generator=g)
     assert torch.allclose(post.log_prob(th, xo), logprob_loop(OracleEnsembleRegressor(**kw), x, theta, xo, th), atol=1e-6)
+
+
+# ---- round 2: pins of the support loop and of sample_batched against the reference's own classes -----------------------
+def _box(lo, hi, d=2):
+    from sbi.utils import BoxUniform  # the shim (oracle/shims/sbi), on sys.path through the ref_pkg fixture
+    return BoxUniform(lo * torch.ones(d), hi * torch.ones(d))
+
+
+def test_reference_sample_batched_equals_mirror(ref_pkg, weights):
+    """`sample_batched` with a prior (npe_pfn.py:362-410: oversample 1.5x, up to 10 rounds, per observation the first
+    in-support draws) of the UNMODIFIED reference over the oracle, against the mirror's cumulative-sum scatter
+    (`npe_pfn_b200.npe_pfn.take_first_n`) fed by the oracle's restatement of `_sample_batched` (:171-251): identical
+    draws and log-probs, observation by observation, over several rejection rounds."""
+    pkg, core = ref_pkg
+    from npe_pfn_b200 import NPE_PFN_Core
+    from oracle.estimator import OracleTabPFNRegressor
+    from oracle.reference_loop import sample_batched_loop
+    theta, x, g = _toy(24, 2, 2, 13)
+    prior = _box(-0.4, 1.1)  # tight box around part of the posterior mass: most observations need several rounds
+    calls = []
+
+    class MirrorOverOracle(NPE_PFN_Core):
+        def _sample_batched(self, xs, n, with_log_prob=False, eps=1e-15, return_device=False, **kw):
+            calls.append((xs.shape[0], n))
+            return sample_batched_loop(OracleTabPFNRegressor(weights=weights), self._x_train, self._theta_train, xs, n,
+                                       with_log_prob=with_log_prob, eps=eps)
+
+    ref = core.NPE_PFN_Core(prior=prior).append_simulations(theta, x)
+    mir = MirrorOverOracle(prior=prior, regressor_init_kwargs={"n_estimators": 1}).append_simulations(theta, x)
+    mir.redraw_all_observations = True  # the reference's literal schedule, so the torch RNG is consumed identically
+    xs = x[:4]
+    torch.manual_seed(7)
+    a, alp = ref.sample_batched(xs, (9,), with_log_prob=True)
+    torch.manual_seed(7)
+    b, blp = mir.sample_batched(xs, (9,), with_log_prob=True)
+    assert len(calls) >= 2, "the case must need more than one rejection round"
+    assert a.shape == (4, 9, 2) and torch.equal(a, b) and torch.allclose(alp, blp, atol=1e-6)
+    assert bool(prior.support.check(b.reshape(-1, 2)).all())
+    torch.manual_seed(8)
+    a = ref.sample_batched(xs, (5,))
+    torch.manual_seed(8)
+    b = mir.sample_batched(xs, (5,))
+    assert torch.equal(a, b)
+    # default schedule (later rounds draw only for the observations that are still short): same first-round content,
+    # every draw inside the support, fewer proposals
+    calls.clear()
+    mir.redraw_all_observations = False
+    torch.manual_seed(7)
+    c = mir.sample_batched(xs, (9,))
+    assert c.shape == (4, 9, 2) and bool(prior.support.check(c.reshape(-1, 2)).all())
+    assert calls[0] == (4, 13) and all(k <= 4 for k, _ in calls[1:])
+    # without a prior: one unfiltered pass (npe_pfn.py:351-358)
+    torch.manual_seed(3)
+    a = core.NPE_PFN_Core(prior=None).append_simulations(theta, x).sample_batched(xs, (3,))
+    torch.manual_seed(3)
+    b = MirrorOverOracle(prior=None, regressor_init_kwargs={"n_estimators": 1}).append_simulations(theta, x).sample_batched(xs, (3,))
+    assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("mode_kwargs", [{"mode": "autoregressive"}, {"mode": "ratio_based", "num_posterior_samples": 30}])
+def test_reference_posterior_support_rejection_equals_mirror(ref_pkg, mode_kwargs):
+    """`PosteriorSupport` in rejection mode (support_posterior.py:13-69, 97-182; with the ratio-based log-prob also
+    `prereject_with_bounds`, :264-309): the reference's class and the mirror, both wrapped around the SAME reference
+    posterior object over the oracle and started from the same torch seed, give the same threshold, the same accepted
+    proposals in the same order, the same acceptance rate, and the same prior top-up when `max_iter` runs out."""
+    pkg, core = ref_pkg
+    import npe_pfn.support_posterior as ref_sp
+    from npe_pfn_b200.support_posterior import PosteriorSupport as Mirror
+    theta, x, g = _toy(24, 2, 2, 17)
+    prior = _box(-2.5, 2.5)
+    obs = x[:1].clone()
+    results = {}
+    for name, cls in (("ref", ref_sp.PosteriorSupport), ("mirror", Mirror)):
+        posterior = pkg.TabPFN_Based_NPE_PFN(prior=prior, filter_type="no_filtering").append_simulations(theta, x)
+        torch.manual_seed(1)
+        ps = cls(prior, posterior, obs, num_samples_to_estimate_support=30, batch_size_for_estimate_support=30,
+                 allowed_false_negatives=0.2, max_iter_rejection=6, log_prob_kwargs=mode_kwargs)
+        torch.manual_seed(2)
+        s, rate = ps.sample((20,), show_progress_bars=False, sampling_batch_size=16, return_acceptance_rate=True)
+        # an (almost) unreachable threshold: the iteration budget runs out and raw prior draws fill the remainder
+        ps.thr = ps.thr + 50.0
+        ps.max_iter = 2
+        torch.manual_seed(3)
+        s2 = ps.sample((6,), show_progress_bars=False, sampling_batch_size=8)
+        results[name] = (ps.thr, s, rate, s2)
+    (thr_a, s_a, r_a, s2_a), (thr_b, s_b, r_b, s2_b) = results["ref"], results["mirror"]
+    assert torch.equal(thr_a, thr_b)
+    assert s_a.shape == (20, 2) and torch.equal(s_a, s_b) and r_a == pytest.approx(r_b)
+    assert s2_a.shape == (6, 2) and torch.equal(s2_a, s2_b)
+
+
+def test_reference_posterior_support_sir_equals_mirror(ref_pkg):
+    """Sampling-importance-resampling mode (support_posterior.py:184-258): groups of `oversample_sir` posterior draws,
+    adaptive log-prob quantile, one categorical pick per group, effective sample sizes."""
+    pkg, core = ref_pkg
+    import npe_pfn.support_posterior as ref_sp
+    from npe_pfn_b200.support_posterior import PosteriorSupport as Mirror
+    theta, x, g = _toy(24, 2, 2, 19)
+    prior = _box(-3.0, 3.0)
+    obs = x[:1].clone()
+    out = {}
+    for name, cls in (("ref", ref_sp.PosteriorSupport), ("mirror", Mirror)):
+        posterior = pkg.TabPFN_Based_NPE_PFN(prior=prior, filter_type="no_filtering").append_simulations(theta, x)
+        ps = cls(prior, posterior, obs, sampling_method="sir", oversample_sir=4, allowed_false_negatives=0.1)
+        torch.manual_seed(5)
+        out[name] = ps.sample((7,), show_progress_bars=False, sampling_batch_size=12, return_ess=True)
+    (s_a, ess_a), (s_b, ess_b) = out["ref"], out["mirror"]
+    assert s_a.shape == (7, 2) and torch.equal(s_a, s_b)
+    assert torch.allclose(ess_a, ess_b, atol=1e-6) and bool((ess_b >= 1 - 1e-5).all()) and bool((ess_b <= 4 + 1e-5).all())
+    assert bool(prior.support.check(s_b).all())
+
+
+def test_reference_tsnpe_rounds_equal_mirror(ref_pkg):
+    """`run_tsnpe_pfn` (tsnpe_pfn.py:14-119) of the reference against the mirror's round driver, both building the
+    REFERENCE's posterior class over the oracle: same simulations round by round (the proposals, the support thresholds
+    and the simulator noise all come from the same torch RNG stream)."""
+    pkg, core = ref_pkg
+    import npe_pfn.tsnpe_pfn as ref_ts
+    import npe_pfn_b200.tsnpe_pfn as mir_ts
+    prior = _box(-2.0, 2.0)
+
+    def simulator(t):
+        return t + 0.1 * torch.randn_like(t)
+
+    kw = dict(num_simulations=36, num_rounds=3, proposal_batch_size=24, simulation_batch_size=12,
+              num_samples_to_estimate_support=24, allowed_false_negatives=0.1, log_prob_mode="autoregressive",
+              max_iter_rejection=5)
+    torch.manual_seed(4)
+    a = ref_ts.run_tsnpe_pfn(simulator, prior, torch.zeros(1, 2), **kw)
+    saved = mir_ts.TabPFN_Based_NPE_PFN
+    mir_ts.TabPFN_Based_NPE_PFN = pkg.TabPFN_Based_NPE_PFN  # the mirror's driver around the reference's posterior class
+    try:
+        torch.manual_seed(4)
+        b = mir_ts.run_tsnpe_pfn(simulator, prior, torch.zeros(1, 2), **kw)
+    finally:
+        mir_ts.TabPFN_Based_NPE_PFN = saved
+    assert a._theta_train.shape == (36, 2)
+    assert torch.equal(a._theta_train, b._theta_train) and torch.equal(a._x_train, b._x_train)
