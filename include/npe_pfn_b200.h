@@ -113,10 +113,38 @@ int pfn_logprob(pfn_ctx* ctx, int slot, const float* X, int64_t ldx, int64_t M, 
  * +-inf; NULL = unbounded) and (mask == NULL or mask[r] != 0) and all finite.
  * out_idx[0..count) = accepted row indices in increasing order; out_rows (may
  * be NULL) receives the accepted rows packed [count, dim] (row stride dim);
- * out_count is a DEVICE int64.  No host sync. */
+ * out_count is a DEVICE int64.  One kernel, predicate evaluated once, no host sync. */
 int pfn_accept_compact(pfn_ctx* ctx, const float* theta, int64_t ld, int64_t M, int dim, const float* lo,
                        const float* hi, const uint8_t* mask, int64_t* out_idx, float* out_rows,
                        int64_t* out_count, void* stream);
+
+/* The same predicate + ordered compaction as ONE link of an on-device rejection loop: accepted rows are APPENDED to
+ * out_rows[capacity, dim] (row stride out_ld) at the device-resident cursor[0], in proposal order; cursor[0] += number
+ * accepted, cursor[1] += M (proposals seen).  Rows past `capacity` are counted but not written, so "the first
+ * num_samples accepted, in proposal order" (accept_reject_sampler.py:82) is what the buffer holds however many rounds
+ * are enqueued.  Optional extras: `score`/`thr` accept only rows with score[r] > *thr (thr is a DEVICE scalar: the TSNPE
+ * truncated-prior rule `log_probs > self.thr`, support_posterior.py:152-154); `logp` is a per-row payload carried into
+ * out_logp.  One kernel (warp ballot + block scan + decoupled look-back), no host sync. */
+int pfn_accept_append(pfn_ctx* ctx, const float* theta, int64_t ld, int64_t M, int dim, const float* lo, const float* hi,
+                      const uint8_t* mask, const float* score, const float* thr, const float* logp, float* out_rows,
+                      int64_t out_ld, float* out_logp, int64_t capacity, int64_t* cursor, void* stream);
+
+/* Prior proposals on a box (`prior.sample((bs,))` for a BoxUniform, support_posterior.py:137, 305-309) drawn on the
+ * device: out[r, j] = lo[j] + u (hi[j] - lo[j]), u = Philox4x32-10(seed; row0 + r, j). */
+int pfn_uniform_box(pfn_ctx* ctx, const float* lo, const float* hi, int64_t M, int dim, uint64_t seed, uint64_t row0,
+                    float* out, int64_t ld, void* stream);
+
+/* The whole accept/reject loop of `NPE_PFN_Core.sample` (npe_pfn.py:284-303 -> accept_reject_sampler.py:48-77) for a box
+ * (or unbounded: lo = hi = NULL) prior support, enqueued WITHOUT any host round trip: `n_rounds` proposal rounds of
+ * `round_rows` rows; each round = autoregressive draw of all `dtheta` dimensions for the observation x_obs[dx]
+ * (`slots` is a HOST array: slots[d] holds the prefilled context of dimension d, F = dx + d), support check, ordered
+ * append at the device cursor (see pfn_accept_append).  The caller reads cursor[0] once when it needs the count.
+ * Philox rows of round k: row0 + k * round_rows + r.  out_logp (optional) receives the summed per-dimension log-prob
+ * (-inf -> log eps per dimension) of the accepted draws. */
+int pfn_sample_rejection(pfn_ctx* ctx, const int32_t* slots, const float* x_obs, int dx, int dtheta, int n_rounds,
+                         int64_t round_rows, const float* lo, const float* hi, uint64_t seed, uint64_t row0, float eps,
+                         float* out_theta, int64_t out_ld, float* out_logp, int64_t capacity, int64_t* cursor,
+                         void* stream);
 
 /* Context filter (support_posterior.py:357-369, called from get_context, npe_pfn.py:739-744): z-score the columns
  * of x_train[Ntot, dx] (row stride ld), L2 distance of every row to obs[dx], indices of the k nearest rows in

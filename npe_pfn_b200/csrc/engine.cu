@@ -77,9 +77,12 @@ struct pfn_ctx {
     bf16* dech = nullptr;
     float* logits = nullptr;
     // compaction scratch
-    int32_t* cp_counts = nullptr;
-    int64_t* cp_offsets = nullptr;
+    unsigned long long* cp_state = nullptr;  // [cp_cap] look-back tile states | 2 ticket words (zeroed per launch)
     int64_t cp_cap = 0;
+    // on-device rejection loop (pfn_sample_rejection): joint test matrix / log-probs of one proposal round
+    float* rj_buf = nullptr;
+    float* rj_logp = nullptr;
+    int64_t rj_rows = 0, rj_ld = 0;
     // context-filter scratch
     uint8_t* flt_ws = nullptr;
     int64_t flt_cap = 0;
@@ -462,8 +465,9 @@ int pfn_ctx_destroy(pfn_ctx* c) {
     cudaFree(c->ws);
     cudaFree(c->dech);
     cudaFree(c->logits);
-    cudaFree(c->cp_counts);
-    cudaFree(c->cp_offsets);
+    cudaFree(c->cp_state);
+    cudaFree(c->rj_buf);
+    cudaFree(c->rj_logp);
     cudaFree(c->flt_ws);
     cudaFree(c->attn_dbg);
     delete c;
@@ -640,6 +644,24 @@ int pfn_logprob(pfn_ctx* c, int slot, const float* X, int64_t ldx, int64_t M, co
                       accumulate, stream);
 }
 
+static int launch_compact(pfn_ctx* c, CompactArgs a, cudaStream_t st) {
+    const int64_t nblocks = ceil_div(a.M, CP_TILE);
+    if (nblocks > c->cp_cap) {
+        PFN_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(c->cp_state);
+        c->cp_state = nullptr; c->cp_cap = 0;
+        PFN_CUDA_OK(cudaMalloc(&c->cp_state, (size_t)(nblocks + 1024 + 1) * 8));
+        c->cp_cap = nblocks + 1024;
+    }
+    PFN_CUDA_OK(cudaMemsetAsync(c->cp_state, 0, (size_t)(nblocks + 1) * 8, st));
+    a.tile_state = c->cp_state;
+    a.ticket = reinterpret_cast<unsigned int*>(c->cp_state + nblocks);
+    TimeScope ts(c, st, KC_COMPACT, 0.0, (double)a.M * a.dim * 4.0);
+    compact_append_kernel<<<(unsigned)nblocks, CP_THREADS, 0, st>>>(a);
+    PFN_LAUNCH_OK(c);
+    return 0;
+}
+
 int pfn_accept_compact(pfn_ctx* c, const float* theta, int64_t ld, int64_t M, int dim, const float* lo, const float* hi,
                        const uint8_t* mask, int64_t* out_idx, float* out_rows, int64_t* out_count, void* stream) {
     PFN_REQUIRE(c && out_count, "null argument");
@@ -651,24 +673,90 @@ int pfn_accept_compact(pfn_ctx* c, const float* theta, int64_t ld, int64_t M, in
         return 0;
     }
     PFN_REQUIRE(theta, "null data pointer");
-    const int64_t nblocks = ceil_div(M, CP_THREADS);
-    if (nblocks > c->cp_cap) {
-        PFN_CUDA_OK(cudaStreamSynchronize(st));
-        cudaFree(c->cp_counts);
-        cudaFree(c->cp_offsets);
-        c->cp_cap = 0;
-        PFN_CUDA_OK(cudaMalloc(&c->cp_counts, (size_t)(nblocks + 1024) * 4));
-        PFN_CUDA_OK(cudaMalloc(&c->cp_offsets, (size_t)(nblocks + 1024) * 8));
-        c->cp_cap = nblocks + 1024;
+    CompactArgs a{};
+    a.theta = theta; a.ld = ld; a.M = M; a.dim = dim; a.lo = lo; a.hi = hi; a.mask = mask;
+    a.out_idx = out_idx; a.out_rows = out_rows; a.out_ld = dim; a.capacity = M; a.out_count = out_count;
+    return launch_compact(c, a, st);
+}
+
+int pfn_accept_append(pfn_ctx* c, const float* theta, int64_t ld, int64_t M, int dim, const float* lo, const float* hi,
+                      const uint8_t* mask, const float* score, const float* thr, const float* logp, float* out_rows,
+                      int64_t out_ld, float* out_logp, int64_t capacity, int64_t* cursor, void* stream) {
+    PFN_REQUIRE(c && cursor, "null argument");
+    PFN_REQUIRE(M >= 0 && dim >= 1 && ld >= dim && out_ld >= dim && capacity >= 0, "bad shape");
+    PFN_REQUIRE((score == nullptr) == (thr == nullptr), "score and thr come together");
+    if (M == 0) return 0;
+    PFN_REQUIRE(theta && out_rows, "null data pointer");
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    CompactArgs a{};
+    a.theta = theta; a.ld = ld; a.M = M; a.dim = dim; a.lo = lo; a.hi = hi; a.mask = mask; a.score = score; a.thr = thr;
+    a.logp = logp; a.out_rows = out_rows; a.out_ld = out_ld; a.out_logp = out_logp; a.capacity = capacity; a.cursor = cursor;
+    return launch_compact(c, a, (cudaStream_t)stream);
+}
+
+int pfn_uniform_box(pfn_ctx* c, const float* lo, const float* hi, int64_t M, int dim, uint64_t seed, uint64_t row0,
+                    float* out, int64_t ld, void* stream) {
+    PFN_REQUIRE(c && lo && hi && (out || M == 0), "null argument");
+    PFN_REQUIRE(M >= 0 && dim >= 1 && ld >= dim, "bad shape");
+    if (M == 0) return 0;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    uniform_box_kernel<<<(unsigned)ceil_div(M, 256), 256, 0, (cudaStream_t)stream>>>(lo, hi, M, dim, seed, row0, out, ld);
+    PFN_LAUNCH_OK(c);
+    return 0;
+}
+
+int pfn_sample_rejection(pfn_ctx* c, const int32_t* slots, const float* x_obs, int dx, int dtheta, int n_rounds,
+                         int64_t round_rows, const float* lo, const float* hi, uint64_t seed, uint64_t row0, float eps,
+                         float* out_theta, int64_t out_ld, float* out_logp, int64_t capacity, int64_t* cursor,
+                         void* stream) {
+    PFN_REQUIRE(c && slots && x_obs && out_theta && cursor, "null argument");
+    PFN_REQUIRE(dx >= 1 && dtheta >= 1 && n_rounds >= 0 && round_rows >= 1 && out_ld >= dtheta && capacity >= 0, "bad shape");
+    for (int d = 0; d < dtheta; ++d) {
+        if (int rc = check_slot(c, slots[d], true)) return rc;
+        PFN_REQUIRE(c->slots[slots[d]].F == dx + d, "slot d must hold the context of dimension d (F = dx + d features)");
     }
-    compact_count_kernel<<<(unsigned)nblocks, CP_THREADS, 0, st>>>(theta, ld, M, dim, lo, hi, mask, c->cp_counts);
-    PFN_LAUNCH_OK(c);
-    compact_scan_kernel<<<1, 1024, 0, st>>>(c->cp_counts, nblocks, c->cp_offsets, out_count);
-    PFN_LAUNCH_OK(c);
-    if (out_idx || out_rows) {
-        compact_scatter_kernel<<<(unsigned)nblocks, CP_THREADS, 0, st>>>(theta, ld, M, dim, lo, hi, mask, c->cp_offsets,
-                                                                       out_idx, out_rows);
+    cudaStream_t st = (cudaStream_t)stream;
+    PFN_CUDA_OK(cudaSetDevice(c->device));
+    if (int rc = ensure_decoder_ws(c)) return rc;
+    const int64_t ld = dx + dtheta;
+    if (round_rows > c->rj_rows || ld > c->rj_ld) {
+        PFN_CUDA_OK(cudaStreamSynchronize(st));
+        cudaFree(c->rj_buf); cudaFree(c->rj_logp);
+        c->rj_buf = nullptr; c->rj_logp = nullptr; c->rj_rows = 0; c->rj_ld = 0;
+        PFN_CUDA_OK(cudaMalloc(&c->rj_buf, (size_t)round_rows * ld * 4));
+        PFN_CUDA_OK(cudaMalloc(&c->rj_logp, (size_t)round_rows * 4));
+        c->rj_rows = round_rows; c->rj_ld = ld;
+    }
+    const int B = c->cfg.num_buckets;
+    const float log_eps = std::log(eps);
+    for (int k = 0; k < n_rounds; ++k) {
+        const uint64_t r0 = row0 + (uint64_t)k * (uint64_t)round_rows;
+        // x_o into every row of the joint test matrix (npe_pfn.py:121-122), log-prob accumulator to zero
+        broadcast_rows_kernel<<<(unsigned)ceil_div(round_rows * dx, 256), 256, 0, st>>>(x_obs, dx, round_rows, c->rj_buf, ld);
         PFN_LAUNCH_OK(c);
+        if (out_logp) PFN_CUDA_OK(cudaMemsetAsync(c->rj_logp, 0, (size_t)round_rows * 4, st));
+        float* lp = out_logp ? c->rj_logp : nullptr;
+        for (int d = 0; d < dtheta; ++d) {
+            Slot& s = c->slots[slots[d]];
+            if (d == 0) {
+                // all rows are the same observation: one forward row, round_rows inverse-CDF draws from its logits
+                if (int rc = forward_rows(c, s, c->rj_buf, ld, nullptr, 1, st)) return rc;
+                if (int rc = decode_rows(c, s, 0, 1, c->logits, B, st)) return rc;
+                HeadArgs h{};
+                h.logits = c->logits; h.ld_logits = 0; h.group = 1; h.M = round_rows; h.B = B; h.borders = s.borders;
+                h.seed = seed; h.row0 = r0; h.offset = 0; h.out_theta = c->rj_buf + dx; h.ld_theta = ld;
+                h.out_logp = lp; h.log_eps = log_eps; h.accumulate = 1;
+                if (int rc = launch_head(c, h, true, st)) return rc;
+            } else {
+                if (int rc = fused_step(c, slots[d], c->rj_buf, ld, round_rows, true, nullptr, seed, r0, (uint64_t)d,
+                                        c->rj_buf + dx + d, ld, nullptr, nullptr, 0, lp, eps, 1, stream))
+                    return rc;
+            }
+        }
+        CompactArgs a{};
+        a.theta = c->rj_buf + dx; a.ld = ld; a.M = round_rows; a.dim = dtheta; a.lo = lo; a.hi = hi; a.logp = lp;
+        a.out_rows = out_theta; a.out_ld = out_ld; a.out_logp = out_logp; a.capacity = capacity; a.cursor = cursor;
+        if (int rc = launch_compact(c, a, st)) return rc;
     }
     return 0;
 }

@@ -675,6 +675,13 @@ __global__ void __launch_bounds__(CP_THREADS) compact_append_kernel(const Compac
     }
 }
 
+// row r of dst[rows, ld] <- src[n] in its first n columns (the observation repeated down the joint test matrix)
+__global__ void broadcast_rows_kernel(const float* __restrict__ src, int n, int64_t rows, float* __restrict__ dst, int64_t ld) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * n) return;
+    dst[(i / n) * ld + (i % n)] = src[i % n];
+}
+
 // uniform proposals on a box (`BoxUniform.sample`, support_posterior.py:137 / :305-309): out[r, j] = lo[j] + u (hi[j] - lo[j]),
 // u from Philox4x32-10 keyed by (seed; counter = (row0 + r, j / 4)), 23-bit mantissa, strictly inside (0, 1)
 __global__ void uniform_box_kernel(const float* __restrict__ lo, const float* __restrict__ hi, int64_t M, int dim, uint64_t seed,

@@ -50,29 +50,40 @@ def reduce_counts(accepted: int, drawn: int, device=None) -> Tuple[int, int]:
     return int(t[0]), int(t[1])
 
 
-def sample_sharded(posterior, num_samples: int, x: torch.Tensor, gather: bool = True, **sample_kwargs):
+def _gather_device(posterior):
+    """device on which the gather runs: the engine's GPU under NCCL, None (host tensors) under gloo"""
+    rank, world = _world()
+    return posterior.engine.device if world > 1 and dist.get_backend() == "nccl" else None
+
+
+def sample_sharded(posterior, num_samples: int, x: torch.Tensor, gather: bool = True, device_result: bool = False,
+                   **sample_kwargs):
     """`posterior.sample((num_samples,), x)` with the draws split over the ranks.
 
     Each rank draws its share with a disjoint Philox row range and (by default) all ranks receive the
-    concatenation in rank order.  Returns (samples, global acceptance rate)."""
+    concatenation in rank order.  `device_result=True` keeps the (gathered) draws on the GPU instead of returning
+    host tensors.  Returns (samples, global acceptance rate)."""
     rank, world = _world()
     lo, hi = shard_bounds(num_samples, world, rank)
     posterior.rank_row_offset = rank << 40
+    if device_result:
+        sample_kwargs = dict(sample_kwargs, return_device=True)
     local = posterior.sample((hi - lo,), x, **sample_kwargs) if hi > lo else None
     with_lp = isinstance(local, tuple)
     acc = getattr(posterior, "last_acceptance_rate", 1.0) or 1.0
-    dev = posterior.engine.device if world > 1 and dist.get_backend() == "nccl" else None
+    dev = _gather_device(posterior)
     n_acc, n_drawn = reduce_counts(hi - lo, int(round((hi - lo) / max(acc, 1e-12))), device=dev)
     rate = n_acc / max(n_drawn, 1)
     if not gather or world == 1:
         return local, rate
+
+    def g(t):
+        t = gather_rows(t.to(dev) if dev is not None else t, num_samples)
+        return t if device_result or dev is None else t.cpu()
+
     if with_lp:
-        s, lp = local
-        if dev is not None:
-            s, lp = s.to(dev), lp.to(dev)
-        return (gather_rows(s, num_samples), gather_rows(lp, num_samples)), rate
-    s = local.to(dev) if dev is not None else local
-    return gather_rows(s, num_samples), rate
+        return (g(local[0]), g(local[1])), rate
+    return g(local), rate
 
 
 def log_prob_sharded(posterior, theta: torch.Tensor, x: torch.Tensor, **kw) -> torch.Tensor:
@@ -81,5 +92,34 @@ def log_prob_sharded(posterior, theta: torch.Tensor, x: torch.Tensor, **kw) -> t
     local = posterior.log_prob(theta[lo:hi], x, **kw)
     if world == 1:
         return local
-    dev = posterior.engine.device if dist.get_backend() == "nccl" else None
-    return gather_rows(local.to(dev) if dev is not None else local, theta.shape[0])
+    dev = _gather_device(posterior)
+    out = gather_rows(local.to(dev) if dev is not None else local, theta.shape[0])
+    return out.cpu() if dev is not None else out
+
+
+def sample_batched_sharded(posterior, x: torch.Tensor, num_samples: int, gather: bool = True, **kw):
+    """`posterior.sample_batched(x, (num_samples,))` with the OBSERVATIONS split over the ranks (BASELINE config 4: many
+    observations against one shared context).  Every rank holds the same simulations, prefills the same per-dimension
+    K/V caches and draws for its contiguous block of observations with a disjoint Philox row range; the per-observation
+    results are gathered in observation order.  -> [num_obs, num_samples, dim_theta] (and log-probs if requested)."""
+    rank, world = _world()
+    num_obs = x.shape[0]
+    lo, hi = shard_bounds(num_obs, world, rank)
+    posterior.rank_row_offset = rank << 40
+    local = posterior.sample_batched(x[lo:hi], (num_samples,), **kw) if hi > lo else None
+    if not gather or world == 1:
+        return local
+    dev = _gather_device(posterior)
+    with_lp = isinstance(local, tuple) or bool(kw.get("with_log_prob"))
+    d_theta = posterior._theta_train.shape[1]
+
+    def g(t, shape):
+        if t is None:
+            t = torch.empty((0,) + shape, dtype=torch.float32)
+        out = gather_rows(t.to(dev) if dev is not None else t, num_obs)
+        return out.cpu() if dev is not None else out
+
+    if with_lp:
+        s, lp = local if local is not None else (None, None)
+        return g(s, (num_samples, d_theta)), g(lp, (num_samples,))
+    return g(local, (num_samples, d_theta))

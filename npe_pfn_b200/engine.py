@@ -30,7 +30,7 @@ class pfn_model_config(ctypes.Structure):
 ABI_SYMBOLS = [
     "pfn_abi_version", "pfn_last_error", "pfn_ctx_create", "pfn_ctx_destroy", "pfn_set_option", "pfn_prefill",
     "pfn_forward_logits", "pfn_head_sample", "pfn_head_nll", "pfn_sample", "pfn_logprob", "pfn_accept_compact",
-    "pfn_filter_context",
+    "pfn_accept_append", "pfn_uniform_box", "pfn_sample_rejection", "pfn_filter_context",
     "pfn_slot_info", "pfn_launch_count", "pfn_kernel_times", "pfn_slot_export", "pfn_slot_state", "pfn_slot_import",
     "pfn_debug_last_states", "pfn_member_transform", "pfn_ensemble_combine", "pfn_attn_debug_counts",
 ]
@@ -86,6 +86,13 @@ def load_library(build_if_missing: bool = True) -> ctypes.CDLL:
     L.pfn_logprob.argtypes = [vp, c.c_int, vp, i64, i64, vp, i64, vp, f32, c.c_int, vp]
     L.pfn_accept_compact.restype = c.c_int
     L.pfn_accept_compact.argtypes = [vp, vp, i64, i64, c.c_int, vp, vp, vp, vp, vp, vp, vp]
+    L.pfn_accept_append.restype = c.c_int
+    L.pfn_accept_append.argtypes = [vp, vp, i64, i64, c.c_int, vp, vp, vp, vp, vp, vp, vp, i64, vp, i64, vp, vp]
+    L.pfn_uniform_box.restype = c.c_int
+    L.pfn_uniform_box.argtypes = [vp, vp, vp, i64, c.c_int, u64, u64, vp, i64, vp]
+    L.pfn_sample_rejection.restype = c.c_int
+    L.pfn_sample_rejection.argtypes = [vp, c.POINTER(i32), vp, c.c_int, c.c_int, c.c_int, i64, vp, vp, u64, u64, f32, vp, i64,
+                                       vp, i64, vp, vp]
     L.pfn_filter_context.restype = c.c_int
     L.pfn_filter_context.argtypes = [vp, vp, i64, i64, c.c_int, vp, i64, vp, vp, vp]
     L.pfn_slot_info.restype = c.c_int
@@ -273,13 +280,63 @@ class Engine:
         idx = torch.empty(M, dtype=torch.int64, device=self.device)
         rows = torch.empty(M, dim, dtype=torch.float32, device=self.device) if want_rows else None
         count = torch.zeros((), dtype=torch.int64, device=self.device)
-        lo = None if lo is None else lo.to(self.device, torch.float32).contiguous()
-        hi = None if hi is None else hi.to(self.device, torch.float32).contiguous()
+        lo, hi = self._bounds(lo, hi, dim)
         mask = None if mask is None else mask.to(self.device, torch.uint8).contiguous()
         self._check(self.lib.pfn_accept_compact(self._h, _ptr(theta), theta.stride(0) if M > 1 else dim, M, dim,
                                                 _ptr(lo), _ptr(hi), _ptr(mask), _ptr(idx), _ptr(rows), _ptr(count),
                                                 self._stream()))
         return idx, rows, count
+
+    def _bounds(self, lo, hi, dim: int):
+        """box bounds as [dim] fp32 device tensors (scalars / broadcastable bounds are expanded: the kernels index them
+        per dimension)"""
+        def fix(b):
+            if b is None:
+                return None
+            b = torch.as_tensor(b, dtype=torch.float32).to(self.device).reshape(-1)
+            if b.numel() == 1:
+                b = b.expand(dim)
+            if b.numel() != dim:
+                raise ValueError(f"support bounds have {b.numel()} entries, theta has {dim} dimensions")
+            return b.contiguous()
+        return fix(lo), fix(hi)
+
+    def accept_append(self, theta: torch.Tensor, out_rows: torch.Tensor, cursor: torch.Tensor, lo=None, hi=None, mask=None,
+                      score=None, thr=None, logp=None, out_logp=None):
+        """One link of an on-device rejection loop: append the accepted rows of `theta` to `out_rows` at `cursor[0]`
+        (device int64[2] = accepted, proposed), in order.  No host synchronisation."""
+        assert theta.is_cuda and theta.dtype == torch.float32 and theta.ndim == 2 and theta.stride(1) == 1
+        assert out_rows.is_cuda and out_rows.dtype == torch.float32 and out_rows.stride(1) == 1
+        assert cursor.is_cuda and cursor.dtype == torch.int64 and cursor.numel() >= 2
+        M, dim = theta.shape
+        lo, hi = self._bounds(lo, hi, dim)
+        mask = None if mask is None else mask.to(self.device, torch.uint8).contiguous()
+        if score is not None:
+            score = score.to(self.device, torch.float32).contiguous()
+            thr = torch.as_tensor(thr, dtype=torch.float32).to(self.device).reshape(1)
+        self._check(self.lib.pfn_accept_append(self._h, _ptr(theta), theta.stride(0) if M > 1 else dim, M, dim, _ptr(lo),
+                                               _ptr(hi), _ptr(mask), _ptr(score), _ptr(thr), _ptr(logp), _ptr(out_rows),
+                                               out_rows.stride(0), _ptr(out_logp), out_rows.shape[0], _ptr(cursor),
+                                               self._stream()))
+
+    def uniform_box(self, lo, hi, M: int, seed: int, row0: int = 0) -> torch.Tensor:
+        lo, hi = self._bounds(lo, hi, int(torch.as_tensor(lo).numel()))
+        out = torch.empty(M, lo.numel(), dtype=torch.float32, device=self.device)
+        self._check(self.lib.pfn_uniform_box(self._h, _ptr(lo), _ptr(hi), M, lo.numel(), seed, row0, _ptr(out), lo.numel(),
+                                             self._stream()))
+        return out
+
+    def sample_rejection(self, slots, x_obs: torch.Tensor, dim_theta: int, n_rounds: int, round_rows: int, out_theta,
+                         cursor, lo=None, hi=None, seed=0, row0=0, eps=1e-15, out_logp=None):
+        """`n_rounds` proposal rounds of the autoregressive sampler + support check + ordered append, enqueued back to
+        back with no host round trip (pfn_sample_rejection)."""
+        x_obs = x_obs.to(self.device, torch.float32).reshape(-1).contiguous()
+        lo, hi = self._bounds(lo, hi, dim_theta)
+        arr = (c.c_int32 * dim_theta)(*[int(s) for s in slots])
+        self._check(self.lib.pfn_sample_rejection(self._h, arr, _ptr(x_obs), x_obs.numel(), dim_theta, int(n_rounds),
+                                                  int(round_rows), _ptr(lo), _ptr(hi), seed, row0, eps, _ptr(out_theta),
+                                                  out_theta.stride(0), _ptr(out_logp), out_theta.shape[0], _ptr(cursor),
+                                                  self._stream()))
 
     def attn_debug_counts(self):
         """(redone fast-path tiles, reference changes, general-path tiles) since set_option("attn_debug", 1)."""

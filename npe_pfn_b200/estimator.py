@@ -264,7 +264,9 @@ class B200TabPFNClassifier:
         self._build()
         return self
 
-    def predict_proba(self, X):
+    def predict_proba(self, X, return_device: bool = False):
+        """class probabilities [m, n_classes]: a numpy array like upstream's, or (`return_device=True`, not in upstream) a
+        CUDA tensor left on the device"""
         if not self.n_classes:
             raise RuntimeError("predict_proba called before fit")
         tags = self.engine.__dict__.setdefault("_slot_tags", {})
@@ -272,6 +274,7 @@ class B200TabPFNClassifier:
             self._build()  # another classifier object fitted into the shared engine since: rebuild OUR context
         X = torch.as_tensor(X, dtype=torch.float32)
         if self._ens is not None:
-            return self._ens.class_probabilities(X.to(self.engine.device)).cpu().numpy()
-        logits = self.engine.forward_logits(0, X)[:, :self.n_classes]
-        return torch.softmax(logits, dim=-1).cpu().numpy()
+            probs = self._ens.class_probabilities(X.to(self.engine.device))
+        else:
+            probs = torch.softmax(self.engine.forward_logits(0, X)[:, :self.n_classes], dim=-1)
+        return probs if return_device else probs.cpu().numpy()

@@ -380,8 +380,9 @@ class NPE_PFN_Core:
     # -- public API -----------------------------------------------------------------------------------------
     def sample(self, sample_shape: torch.Size = torch.Size(), x: Tensor = None, max_sampling_batch_size: int = 10_000,
                with_log_prob: bool = False, eps=1e-15, max_iter_rejection: int | None = None,
-               show_progress_bars: bool = False) -> Tensor | tuple[Tensor, Tensor]:
-        """Sample p(theta | x) for ONE observation with prior-support rejection (npe_pfn.py:253-308)."""
+               show_progress_bars: bool = False, return_device: bool = False) -> Tensor | tuple[Tensor, Tensor]:
+        """Sample p(theta | x) for ONE observation with prior-support rejection (npe_pfn.py:253-308).
+        `return_device=True` (not in the reference) leaves the result on the GPU instead of copying it to the host."""
         if self.embedding_net:
             x = x.reshape(-1, *self.x_shape)
             x = self.embedding_net(x)
@@ -395,19 +396,12 @@ class NPE_PFN_Core:
                                 return_device=True)
 
         num_samples = torch.Size(sample_shape).numel()
-        if self.prior is not None and self._bounds() == (None, None) and max_iter_rejection is None:
-            # the prior's support is all of R^d: every (finite) draw is accepted, so the rejection loop degenerates to
-            # ceil(S / max_sampling_batch_size) proposal rounds with nothing to compact and no host synchronisation
-            parts, lps = [], []
-            for i in range(0, num_samples, max_sampling_batch_size):
-                t, lp = proposal_fn(min(max_sampling_batch_size, num_samples - i))
-                parts.append(t)
-                lps.append(lp)
-            self.last_acceptance_rate = 1.0
-            samples = (torch.cat(parts) if len(parts) > 1 else parts[0]).cpu() if parts else torch.empty(0, 0)
-            if with_log_prob:
-                return samples, (torch.cat(lps) if len(lps) > 1 else lps[0]).cpu()
-            return samples
+        if self.prior is not None and self._bounds() is not None and max_iter_rejection is None:
+            # the prior's support is a box (or all of R^d): the whole accept/reject loop runs on the device
+            samples, log_probs = self._sample_rejection_device(num_samples, x, max_sampling_batch_size, with_log_prob, eps)
+            if return_device:
+                return (samples, log_probs) if with_log_prob else samples
+            return (samples.cpu(), log_probs.cpu()) if with_log_prob else samples.cpu()
 
         samples, log_probs, _ar = accept_reject_sample(
             proposal=proposal_fn,
@@ -419,10 +413,77 @@ class NPE_PFN_Core:
             max_iter_rejection=max_iter_rejection,
         )
         self.last_acceptance_rate = _ar
-        samples = samples.cpu()
+        if not return_device:
+            samples = samples.cpu()
+            log_probs = log_probs.cpu() if log_probs is not None else None
         if with_log_prob:
-            return samples, log_probs.cpu()
+            return samples, log_probs
         return samples
+
+    def _sample_rejection_device(self, num_samples: int, x: Tensor, max_sampling_batch_size: int, with_log_prob: bool,
+                                 eps: float):
+        """Prior-support rejection (npe_pfn.py:284-303 -> accept_reject_sampler.py:43-91) with NO per-round host round trip.
+
+        The reference reads the accepted count back after every proposal round to size the next one
+        (`accept_reject_sampler.py:62-72`).  Here rounds are enqueued in batches: the support check and the ordered
+        compaction append accepted draws to the result at a device-resident cursor (`pfn_sample_rejection` /
+        `pfn_accept_append`), and the host reads the cursor once per BATCH of rounds.  The batch is sized from the
+        acceptance rate remembered for this context (1.0 before anything is known - exact when the support is all of
+        R^d), with the reference's 1.5x overdraw from the second batch on, so a call costs one read-back when the rate
+        is known or 1.0, two when it is met for the first time.  What is returned is what the reference returns: the
+        FIRST `num_samples` accepted draws in proposal order.  `self.last_sync_count` records the read-backs."""
+        ctx = self._prepare_context(x)
+        if self.shard_prefill:
+            self.prefill_sharded(x)
+        eng = self.engine
+        dev = eng.device
+        dx, dth = ctx.dim_x, ctx.dim_theta
+        lo, hi = self._bounds()
+        out = torch.empty(max(num_samples, 1), dth, dtype=torch.float32, device=dev)
+        out_lp = torch.empty(max(num_samples, 1), dtype=torch.float32, device=dev) if with_log_prob else None
+        cursor = torch.zeros(2, dtype=torch.int64, device=dev)
+        rates = self.__dict__.setdefault("_acc_rate", {})
+        rate = 1.0 if (lo is None and hi is None) else rates.get(ctx.key, 1.0)
+        seed = draw_seed()
+        row0 = self.rank_row_offset
+        xd = x.to(dev, torch.float32)
+        native = self._model.n_estimators == 1 and dth <= eng.max_slots
+        slots = [self._ensure_slot(ctx, d) for d in range(dth)] if native else None
+        if native:
+            assert len(set(slots)) == dth, "the engine needs one slot per parameter dimension (max_slots >= dim_theta)"
+        accepted = proposed = syncs = 0
+        first = True
+        self.last_round_log = []  # (first Philox row, rows per round, rounds) of every enqueued batch
+        while accepted < num_samples:
+            missing = num_samples - accepted
+            want = missing / max(rate, 1e-6) * (1.0 if first else 1.5)
+            round_rows = int(min(max_sampling_batch_size, max(math.ceil(want), 100 if not first else 1)))
+            n_rounds = int(min(max(math.ceil(want / round_rows), 1), 4096))
+            self.last_round_log.append((row0 + proposed, round_rows, n_rounds))
+            if native:
+                eng.sample_rejection(slots, xd, dth, n_rounds, round_rows, out, cursor, lo=lo, hi=hi, seed=seed,
+                                     row0=row0 + proposed, eps=eps, out_logp=out_lp)
+            else:  # member ensembles: rounds driven from here, still appended on the device without a read-back
+                for k in range(n_rounds):
+                    saved, self.rank_row_offset = self.rank_row_offset, row0 + proposed + k * round_rows
+                    try:
+                        cand, lp = self._sample(round_rows, x, with_log_prob=with_log_prob, eps=eps, seed=seed,
+                                                return_device=True)
+                    finally:
+                        self.rank_row_offset = saved
+                    eng.accept_append(cand.contiguous(), out, cursor, lo=lo, hi=hi, logp=lp, out_logp=out_lp)
+            proposed += n_rounds * round_rows
+            accepted = int(cursor[0].item())  # the one read-back of this batch of rounds
+            syncs += 1
+            rate = max(accepted / proposed, 1e-6)
+            first = False
+        if proposed:
+            rates[ctx.key] = accepted / proposed
+            self.last_acceptance_rate = accepted / proposed
+        else:
+            self.last_acceptance_rate = 1.0
+        self.last_sync_count = syncs
+        return out[:num_samples], (out_lp[:num_samples] if with_log_prob else None)
 
     def sample_batched(self, x: Tensor, sample_shape: torch.Size = torch.Size(), max_sampling_batch_size: int = 10_000,
                        with_log_prob: bool = False, eps: float = 1e-15, oversample_factor: float = 1.5,
@@ -498,12 +559,32 @@ class NPE_PFN_Core:
     def log_prob_batched(self, theta: Tensor, x: Tensor):
         raise NotImplementedError
 
+    def _log_prob_device(self, theta: Tensor, x: Tensor, mode: str = "autoregressive", eps: float = 1e-15,
+                         **ratio_kwargs) -> Tensor:
+        """`log_prob` for DEVICE-resident `theta`, result left on the device (the TSNPE proposal loop,
+        support_posterior.py:139-149, evaluates every prior proposal with it and never needs the values on the host).
+        The engine chunks the rows itself, so there is no `max_sampling_batch_size` loop and no re-fit per chunk."""
+        x = self._validate_x(x)
+        if mode == "autoregressive":
+            return self._autoregressive_log_prob(theta, x, eps=eps, return_device=True)
+        if mode == "ratio_based":
+            self._ensure_ratio_classifier(x, **{k: v for k, v in ratio_kwargs.items() if k != "eps"})
+            return self._model_classifier.ratio_log_probs_device(theta, eps)
+        raise ValueError(f"Invalid mode: {mode}")
+
     def _ratio_based_log_prob(self, theta: Tensor, x: Tensor = None, num_posterior_samples: int = 5000,
                               boundary_padding: float = 0.1, reuse_estimator_if_possible: bool = True,
                               eps: float = 1e-15) -> Tensor:
         """log p(theta | x) by density-ratio estimation (npe_pfn.py:526-570): a classifier separates posterior
         draws from uniform draws on their padded bounding box; log p = log U + log(p1 + eps) - log(p0 + eps).
         The classifier is re-fitted only when the observation, the context or the two parameters changed."""
+        self._ensure_ratio_classifier(x, num_posterior_samples, boundary_padding, reuse_estimator_if_possible)
+        return self._model_classifier.ratio_log_probs(theta, eps)
+
+    def _ensure_ratio_classifier(self, x: Tensor, num_posterior_samples: int = 5000, boundary_padding: float = 0.1,
+                                 reuse_estimator_if_possible: bool = True):
+        """(re)fit the posterior-vs-uniform classifier when the observation, the context or the parameters changed
+        (npe_pfn.py:554-566)"""
         if self._model_classifier is None:
             self._model_classifier = DensityRatioWrapper(**self.classifier_init_kwargs)
         theta_context, x_context = self.get_context(x)
@@ -512,7 +593,6 @@ class NPE_PFN_Core:
                                                                       num_posterior_samples, boundary_padding):
             draws = self.sample(sample_shape=torch.Size([num_posterior_samples]), x=x)
             wrapper.fit(x, draws, boundary_padding, x_context, theta_context)
-        return wrapper.ratio_log_probs(theta, eps)
 
     def _get_classifier_bounds(self):
         if self._model_classifier is None:
@@ -637,6 +717,19 @@ class DensityRatioWrapper:
 
         return not (same(x, x0) and same(x_context, xc0) and same(theta_context, tc0)
                     and num_posterior_samples == n0 and math.isclose(boundary_padding, pad0))
+
+    def ratio_log_probs_device(self, theta: Tensor, eps=1e-15) -> Tensor:
+        """`ratio_log_probs` for device-resident theta, result on the device and no host synchronisation: the classifier
+        runs on every row and rows outside the padded box are overwritten with the floor value afterwards (the
+        reference indexes the inside rows first, npe_pfn.py:691-697, which needs their count on the host)."""
+        dev = theta.device
+        lo, hi = self._padded_dim_min.to(dev), self._padded_dim_max.to(dev)
+        inside = ((theta >= lo) & (theta <= hi)).all(dim=1)
+        u = float(self._uniform_log_prob)
+        floor = u + math.log(eps) - math.log1p(eps)
+        probs = self._classifier.predict_proba(theta, return_device=True)
+        val = u + torch.log(probs[:, 1] + eps) - torch.log(probs[:, 0] + eps)
+        return torch.where(inside, val, torch.full_like(val, floor))
 
     def ratio_log_probs(self, theta: Tensor, eps=1e-15) -> Tensor:
         inside = ((theta >= self._padded_dim_min) & (theta <= self._padded_dim_max)).all(dim=1)

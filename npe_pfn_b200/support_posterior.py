@@ -87,11 +87,72 @@ class PosteriorSupport:
             assert torch.allclose(lo, new_lo) and torch.allclose(hi, new_hi)
         return cand, lp, (new_lo, new_hi), pre_rate
 
+    #: run the proposal loop on the GPU when the prior is a uniform box and the posterior is engine-backed
+    device_rejection = True
+
+    def _sample_rejection_device(self, wanted: int, sampling_batch_size: int):
+        """The truncated-prior proposal loop (support_posterior.py:133-160) without a host round trip per round: uniform
+        proposals are drawn on the device (`pfn_uniform_box`; inside the classifier's padded box intersected with the
+        prior box when the posterior has one, which is what `prereject_with_bounds` does for a uniform prior,
+        :305-309), their posterior log-prob stays on the device (`NPE_PFN_Core._log_prob_device`), and
+        `log_prob > thr` + ordered compaction append the accepted proposals at a device cursor (`pfn_accept_append`).
+        Rounds are enqueued in batches sized by the running acceptance rate; the host reads the cursor once per batch.
+        -> (accepted [<= wanted, d] on the device, log-prob acceptance rate, pre-acceptance rate, rounds used)"""
+        post = self._posterior
+        eng = post.engine
+        dev = eng.device
+        p_lo, p_hi = get_uniform_bounds(self._prior)
+        kw = dict(self._log_prob_kwargs)
+        mode = kw.pop("mode", "autoregressive")
+        box_lo, box_hi, pre_rate = p_lo, p_hi, 1.0
+        if mode == "ratio_based":
+            post._ensure_ratio_classifier(post._validate_x(self._obs), **{k: v for k, v in kw.items() if k != "eps"})
+            c_lo, c_hi = post._get_classifier_bounds()
+            box_lo, box_hi = torch.max(c_lo, p_lo), torch.min(c_hi, p_hi)
+            # volume fraction of the prior box inside the classifier's box (the reference estimates it from 10^6 raw draws)
+            pre_rate = float(torch.clamp(box_hi - box_lo, min=0).div(p_hi - p_lo).prod())
+        d = p_lo.numel()
+        out = torch.empty(max(wanted, 1), d, dtype=torch.float32, device=dev)
+        cursor = torch.zeros(2, dtype=torch.int64, device=dev)
+        from .estimator import draw_seed
+        seed = draw_seed()
+        accepted = proposed = rounds = 0
+        rate, first = 1.0, True
+        self.last_sync_count = 0
+        while accepted < wanted and rounds < self.max_iter:
+            need = (wanted - accepted) / (rate * sampling_batch_size) * (1.0 if first else 1.5)
+            n_rounds = int(min(self.max_iter - rounds, max(1, -(-need // 1))))
+            for k in range(n_rounds):
+                cand = eng.uniform_box(box_lo, box_hi, sampling_batch_size, seed, row0=proposed + k * sampling_batch_size)
+                lp = post._log_prob_device(cand, self._obs, mode=mode, **kw)
+                eng.accept_append(cand, out, cursor, score=lp, thr=self.thr)
+            rounds += n_rounds
+            proposed += n_rounds * sampling_batch_size
+            accepted = int(cursor[0].item())  # one read-back per batch of rounds
+            self.last_sync_count += 1
+            rate = max(accepted / proposed, 1e-6)
+            first = False
+        return out[:min(accepted, wanted)], accepted / max(proposed, 1), pre_rate, rounds
+
+    def _device_path_ok(self) -> bool:
+        return (self.device_rejection and check_for_uniform(self._prior) and hasattr(self._posterior, "_log_prob_device")
+                and self._log_prob_kwargs.get("mode", "autoregressive") in ("autoregressive", "ratio_based")
+                and torch.cuda.is_available())
+
     def sample_rejection(self, sample_shape: torch.Size = torch.Size(), show_progress_bars: bool = True,
                          sampling_batch_size: int = 10_000, return_acceptance_rate: bool = False):
         shape = torch.Size(sample_shape)
         assert len(shape) == 1, "only 1-D sample shapes are supported"
         wanted = shape[0]
+        if self._device_path_ok():
+            good, lp_rate, pre_rate, _rounds = self._sample_rejection_device(wanted, sampling_batch_size)
+            kept = [good.cpu()]
+            overall = pre_rate * lp_rate
+            log.info("pre-acceptance %.4g, log-prob acceptance %.4g, overall %.4g", pre_rate, lp_rate, overall)
+            if good.shape[0] < wanted:  # iteration budget exhausted: fill with unrestricted prior draws (:171-174)
+                kept.append(self._prior.sample((wanted - good.shape[0],)))
+            out = torch.cat(kept)[:wanted]
+            return (out, overall) if return_acceptance_rate else out
         bar = tqdm(disable=not show_progress_bars, total=wanted, desc=f"Drawing {wanted} restricted posterior samples")
         kept, n_kept, n_proposed = [], 0, 0
         box: Tuple[Optional[Tensor], Optional[Tensor]] = (None, None)

@@ -192,3 +192,116 @@ def test_sample_batched_vs_oracle_loop(engine, weights):
     assert torch.equal(a, b) and torch.equal(alp, blp) and not torch.equal(a[0], a[1])
     for o in range(num_obs):
         assert (post.log_prob(a[o], xs[o:o + 1]) - alp[o]).abs().max() <= 1e-3
+
+
+def test_accept_append_cursor(engine):
+    """pfn_accept_append: ordered append at a device cursor over several calls, capacity clipping, score > thr rule,
+    payload; pfn_accept_compact (same kernel) against torch on ragged sizes incl. multi-tile streams."""
+    g = torch.Generator().manual_seed(3)
+    dim, cap = 3, 700
+    out = torch.full((cap, dim), float("nan"), device="cuda")
+    out_lp = torch.full((cap,), float("nan"), device="cuda")
+    cursor = torch.zeros(2, dtype=torch.int64, device="cuda")
+    lo, hi = torch.full((dim,), -1.0), torch.tensor(1.5)  # scalar upper bound: expanded to [dim]
+    want_rows, want_lp, proposed = [], [], 0
+    for M in (1, 255, 1024, 1025, 5000):
+        th = (torch.rand(M, dim, generator=g) * 4 - 2).cuda()
+        if M > 10:
+            th[7, 0] = float("nan")
+        score = torch.randn(M, generator=g).cuda()
+        lp = torch.randn(M, generator=g).cuda()
+        engine.accept_append(th, out, cursor, lo=lo, hi=hi, score=score, thr=torch.tensor(-0.3), logp=lp, out_logp=out_lp)
+        ok = ((th >= -1.0) & (th <= 1.5)).all(1) & torch.isfinite(th).all(1) & (score > -0.3)
+        want_rows.append(th[ok])
+        want_lp.append(lp[ok])
+        proposed += M
+    want_rows, want_lp = torch.cat(want_rows), torch.cat(want_lp)
+    assert cursor.tolist() == [want_rows.shape[0], proposed] and want_rows.shape[0] > cap  # counted past the capacity
+    assert torch.equal(out, want_rows[:cap]) and torch.equal(out_lp, want_lp[:cap])       # ... but not written
+    for M, d in [(1, 2), (1023, 1), (1024, 4), (300_007, 5)]:
+        th = (torch.rand(M, d, generator=g) * 4 - 2).cuda()
+        idx, rows, count = engine.accept_compact(th, lo=torch.full((d,), -1.0), hi=torch.full((d,), 1.0))
+        ok = ((th >= -1.0) & (th <= 1.0)).all(1)
+        k = int(count)
+        assert k == int(ok.sum()) and torch.equal(idx[:k], torch.nonzero(ok).squeeze(1)) and torch.equal(rows[:k], th[ok])
+    with pytest.raises(ValueError):
+        engine.accept_compact(torch.zeros(4, 3, device="cuda"), lo=torch.zeros(2))
+
+
+def test_device_rejection_loop(engine):
+    """`sample` with a box prior: the accept/reject loop runs on the device (pfn_sample_rejection) and returns the FIRST
+    num_samples accepted draws in proposal order (accept_reject_sampler.py:82) - checked by regenerating the very same
+    proposal stream with `_sample` and filtering it on the host - with at most two read-backs of the cursor on the first
+    call and one once the acceptance rate of the context is known."""
+    from npe_pfn_b200 import BoxUniform, NPE_PFN_Core
+    theta, x, g = _toy(80, 2, 3, 41)
+    box = BoxUniform(torch.tensor([-0.5, -2.0, -1.0]), torch.tensor([1.5, 0.7, 2.5]))
+    post = NPE_PFN_Core(prior=box, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    xo = x[:1].clone()
+    S, max_bs = 700, 256
+    torch.manual_seed(123)
+    s, lp = post.sample((S,), xo, max_sampling_batch_size=max_bs, with_log_prob=True)
+    assert s.shape == (S, 3) and lp.shape == (S,) and bool(box.support.check(s).all())
+    assert post.last_sync_count <= 2 and 0 < post.last_acceptance_rate < 1
+    log = list(post.last_round_log)
+    torch.manual_seed(123)
+    from npe_pfn_b200.estimator import draw_seed
+    seed = draw_seed()
+    stream, stream_lp = [], []
+    for row0, rows, n_rounds in log:
+        for k in range(n_rounds):
+            post.rank_row_offset = row0 + k * rows
+            c, clp = post._sample(rows, xo, with_log_prob=True, seed=seed)
+            stream.append(c)
+            stream_lp.append(clp)
+    post.rank_row_offset = 0
+    stream, stream_lp = torch.cat(stream), torch.cat(stream_lp)
+    ok = box.support.check(stream)
+    assert int(ok.sum()) >= S
+    assert torch.equal(s, stream[ok][:S]) and torch.equal(lp, stream_lp[ok][:S])
+    assert (post.log_prob(s, xo) - lp).abs().max() <= 1e-3
+    # second call on the same context: the remembered rate sizes the batch, one read-back suffices
+    s2 = post.sample((S,), xo, max_sampling_batch_size=max_bs)
+    assert post.last_sync_count == 1 and bool(box.support.check(s2).all()) and not torch.equal(s, s2)
+    # unbounded support: every draw accepted, the result IS the proposal stream, one read-back
+    mvn = torch.distributions.MultivariateNormal(torch.zeros(3), torch.eye(3))
+    post2 = NPE_PFN_Core(prior=mvn, regressor_init_kwargs={"engine": engine}).append_simulations(theta, x)
+    torch.manual_seed(5)
+    a = post2.sample((300,), xo, max_sampling_batch_size=128)
+    torch.manual_seed(5)
+    seed = draw_seed()
+    parts = []
+    for row0, rows, n_rounds in post2.last_round_log:
+        for k in range(n_rounds):
+            post2.rank_row_offset = row0 + k * rows
+            parts.append(post2._sample(rows, xo, seed=seed)[0])
+    post2.rank_row_offset = 0
+    assert post2.last_sync_count == 1 and torch.equal(a, torch.cat(parts)[:300])
+    # the reference's host loop is still there for what the device loop does not cover (max_iter_rejection)
+    s3 = post.sample((50,), xo, max_sampling_batch_size=40, max_iter_rejection=50)
+    assert s3.shape == (50, 3)
+
+
+@pytest.mark.parametrize("mode_kwargs", [{"mode": "autoregressive"}, {"mode": "ratio_based", "num_posterior_samples": 300}])
+def test_posterior_support_device_loop(engine, mode_kwargs):
+    """TSNPE truncated-prior proposals (support_posterior.py:97-182) with the loop on the device: every returned proposal
+    lies in the prior box (and in the classifier box in ratio mode) and has posterior log-prob above the threshold; the
+    host loop of the same object accepts at a compatible rate."""
+    from npe_pfn_b200 import BoxUniform, PosteriorSupport, TabPFN_Based_NPE_PFN
+    theta, x, g = _toy(120, 2, 2, 43)
+    prior = BoxUniform(-3 * torch.ones(2), 3 * torch.ones(2))
+    post = TabPFN_Based_NPE_PFN(prior=prior, filter_type="no_filtering", regressor_init_kwargs={"engine": engine})
+    post.append_simulations(theta, x)
+    obs = x[:1].clone()
+    torch.manual_seed(0)
+    ps = PosteriorSupport(prior, post, obs, num_samples_to_estimate_support=400, batch_size_for_estimate_support=400,
+                          allowed_false_negatives=0.05, log_prob_kwargs=mode_kwargs)
+    s, rate = ps.sample((500,), show_progress_bars=False, sampling_batch_size=1000, return_acceptance_rate=True)
+    assert s.shape == (500, 2) and s.device.type == "cpu" and bool(prior.support.check(s).all())
+    assert ps.last_sync_count <= 3 and 0 < rate <= 1
+    lp = post.log_prob(s, obs, **mode_kwargs)
+    assert float((lp > ps.thr - 1e-4).float().mean()) >= 0.995  # chunked host log_prob vs device: rounding at the threshold
+    ps.device_rejection = False
+    s_h, rate_h = ps.sample((500,), show_progress_bars=False, sampling_batch_size=1000, return_acceptance_rate=True)
+    assert s_h.shape == (500, 2) and abs(rate - rate_h) <= 0.5 * max(rate, rate_h) + 0.02
+    assert (s.mean(0) - s_h.mean(0)).abs().max() <= 0.35 * s_h.std(0).max()
