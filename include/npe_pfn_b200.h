@@ -64,7 +64,8 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
                    void* stream, pfn_ctx** out);
 int pfn_ctx_destroy(pfn_ctx* ctx);
 /* runtime switches (no reference counterpart): "attn_impl" / "gemm_impl" 0 = warp-level mma.sync kernels,
- * 1 = tcgen05/TMEM/TMA kernels (default); "mlp_fused" 1 (default) = MLP sub-layer in one kernel (hidden activation stays on chip), 0 = two GEMM launches; "chunk_rows" = test rows per pass; "standardize_y" 0 = targets enter the y-encoder unscaled (classifier head:
+ * 1 = tcgen05/TMEM/TMA kernels (default); "attn_impl" 2 = attn_tc6 for test rows (row sum on the tensor core, two query
+ * tiles per CTA; measured slower than 1, kept as a parity-tested opt-in); "mlp_fused" 1 (default) = MLP sub-layer in one kernel (hidden activation stays on chip), 0 = two GEMM launches; "chunk_rows" = test rows per pass; "standardize_y" 0 = targets enter the y-encoder unscaled (classifier head:
  * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes; "attn_lean" 2 (default) / 1 = reference maximum folded
  * into the Q K^T MMA + overflow check instead of the maximum pass (1: every reference change redoes / slows the warp's tile, 2: kept on the
  * fast path), 0 = explicit maximum pass per tile; "time_kernels" 1 = record a

@@ -17,6 +17,7 @@
 #include "attn_mma.cuh"
 #ifdef PFN_WITH_ATTN_TC
 #include "attn_tc.cuh"
+#include "attn_tc6.cuh"
 #endif
 #include "common.cuh"
 #include "gemm_mma.cuh"
@@ -205,7 +206,10 @@ int gemm(pfn_ctx* c, const GemmArgs& a, cudaStream_t st) {
 int item_attention(pfn_ctx* c, const AttnArgs& a, int T, cudaStream_t st) {
     TimeScope ts(c, st, a.k_head ? KC_ATTN_CTX : KC_ATTN_TEST, 4.0 * (double)a.R * kHeads * T * (double)a.N * kDh);
 #ifdef PFN_WITH_ATTN_TC
-    if (c->attn_impl == 1) {
+    if (c->attn_impl == 2 && a.k_head == 0 && !c->attn_persist) {
+        // v6 (attn_tc6.cuh): test rows against the cached K/V, row sum on the tensor core, two query tiles per CTA
+        PFN_CUDA_OK(launch_attn_tc6(a, kHeads, T, c->attn_poly % 100, (uint32_t)c->attn_wait_ticks, c->attn_debug ? c->attn_dbg : nullptr, st));
+    } else if (c->attn_impl >= 1) {
         PFN_CUDA_OK(launch_attn_tc(a, kHeads, T, c->attn_poly + 1000 * (c->attn_persist ? 0 : c->attn_lean), c->num_sms, c->attn_persist, (uint32_t)c->attn_wait_ticks, (uint32_t)c->attn_stagger_ns,
                                        c->attn_debug ? c->attn_dbg : nullptr, st));
     } else
@@ -426,7 +430,7 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
         delete c;
         return 2;
     }
-    if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
+    if (const char* e = getenv("NPE_PFN_B200_ATTN")) c->attn_impl = (strcmp(e, "mma") == 0) ? 0 : (strcmp(e, "tc5") == 0) ? 1 : (strcmp(e, "tc6") == 0) ? 2 : c->attn_impl;
     if (const char* e = getenv("NPE_PFN_B200_GEMM")) c->gemm_impl = (strcmp(e, "mma") == 0) ? 0 : 1;
     if (const char* e = getenv("NPE_PFN_B200_ATTN_LEAN")) c->attn_lean = atoi(e);
     if (const char* e = getenv("NPE_PFN_B200_MLP_FUSED")) c->mlp_fused = atoi(e);

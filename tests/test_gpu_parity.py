@@ -359,6 +359,28 @@ def test_full_size_properties(engine):
     assert post.engine.slot_info(9)["N"] == N and post.engine.slot_info(9)["T"] == 11
 
 
+def test_item_attention_v6_agrees(engine, weights):
+    """attn_tc6 (row sum on the tensor core, two query tiles per CTA; opt-in `attn_impl = 2`, slower than v5 and therefore
+    not the default - profiles/r2_attn_tc6_experiments.txt) against v5 and against the fp32 oracle, ragged sizes included."""
+    from oracle.estimator import OracleTabPFNRegressor
+    g = torch.Generator().manual_seed(66)
+    for (N, F, M) in ((1500, 5, 700), (70, 3, 129), (64, 2, 1)):
+        Xc = torch.randn(N, F, generator=g)
+        yc = Xc[:, 1] + 0.1 * torch.randn(N, generator=g)
+        Xt = torch.randn(M, F, generator=g)
+        outs = []
+        for impl in (1, 2):
+            engine.set_option("attn_impl", impl)
+            engine.prefill(5, Xc, yc)
+            outs.append(engine.forward_logits(5, Xt).cpu())
+        engine.set_option("attn_impl", 1)
+        ref = OracleTabPFNRegressor(weights=weights).fit(Xc, yc).predict(Xt)["logits"]
+        d56, d6 = (outs[0] - outs[1]).abs(), (outs[1] - ref).abs()
+        print(f"N={N}: v5 vs v6 max {d56.max():.4f} mean {d56.mean():.5f} | v6 vs fp32 oracle max {d6.max():.4f} mean {d6.mean():.5f}")
+        assert torch.isfinite(outs[1]).all()
+        assert d6.max() <= LOGIT_ATOL and d6.mean() <= LOGIT_MEAN_ATOL and d56.mean() <= LOGIT_MEAN_ATOL
+
+
 def test_item_attention_impls_agree(engine):
     """tcgen05 item attention against the warp-level mma.sync implementation (both bf16 in, fp32 accumulate)."""
     g = torch.Generator().manual_seed(33)
