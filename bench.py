@@ -23,7 +23,7 @@ over NCCL inside the timed region.
                two_moons in full and gaussian_linear over ALL ten dimensions with a re-fit per dimension at reduced M.
 `--impl reference` times that CPU path alone (the reference's arithmetic dependency `tabpfn` is not installable
 offline, so the oracle port stands in; DESIGN.md "reference arm"): every step is one full 10-dimension
-`sample_loop` call at N = 10 000 with M = 256 draws, measured by wall clock, never extrapolated.
+`sample_loop` call at N = 10 000 with M = 1024 draws, measured by wall clock, never extrapolated.
 """
 from __future__ import annotations
 
@@ -49,7 +49,8 @@ import torch  # noqa: E402
 METRIC = "posterior samples/sec (autoregressive, 10k simulations)"
 DIM_X, DIM_THETA, N_CTX = 10, 10, 10_000
 E, L, HID, BUCKETS = 192, 12, 768, 5000
-CPU_M = 256  # draws per CPU reference step (the reference's own default is 10 000 per fit; see cpu_baseline.sample)
+CPU_M = 256      # draws of the cpu_baseline leg inside the default run (the reference's own default is 10 000 per fit)
+REF_M = 1024     # draws per step of the --impl reference arm (one ~2 minute step fits its wall-clock budget)
 
 
 # ---- workloads ------------------------------------------------------------------------------------------------------
@@ -226,7 +227,7 @@ def run_reference_arm(args):
     t_start = time.perf_counter()
     steps = []
     while len(steps) < max(args.steps, 1):
-        steps.append(cpu_step_gaussian_linear())
+        steps.append(cpu_step_gaussian_linear(REF_M))
         spent = time.perf_counter() - t_start
         if spent + steps[-1][0] > args.ref_budget:
             break
@@ -241,10 +242,10 @@ def run_reference_arm(args):
         "steps": len(steps), "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup,
         "ms_per_step": 1000.0 * dt / len(steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"gaussian_linear: 10-D theta / 10-D x, 10k simulations, {CPU_M} posterior draws per step "
+        "config": {"workload": f"gaussian_linear: 10-D theta / 10-D x, 10k simulations, {REF_M} posterior draws per step "
                                "via the reference's autoregressive loop on the host CPU (all 10 dimensions, re-fit per "
                                "dimension), wall clock; steps bounded by a time budget",
-                   "samples_per_step": CPU_M, "context_rows": N_CTX, "n_estimators": 1,
+                   "samples_per_step": REF_M, "context_rows": N_CTX, "n_estimators": 1,
                    "weights": "seeded random init of the TabPFNv2 regressor architecture"},
         "cpu_baseline": rec,
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -259,7 +260,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=100_000, help="posterior draws per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--ref-budget", type=float, default=150.0, help="wall-clock budget (s) of the reference arm")
+    ap.add_argument("--ref-budget", type=float, default=170.0, help="wall-clock budget (s) of the reference arm")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the extra BASELINE.json workloads")
     ap.add_argument("--attn", default=None, choices=[None, "mma", "tc"])

@@ -1,0 +1,302 @@
+// Bar-distribution head, round-2 kernels (same arithmetic spec as oracle/bar_head.c and head_kernel in small_kernels.cuh,
+// hence the same bits: bucket masses are integers, so every partition of the prefix sums gives the same bucket).
+//
+//  head_row_kernel   one CTA (4 warps) per logits row, the row lives in REGISTERS (10 coalesced float4 loads per
+//                    thread, 20 000 B read exactly once, no shared-memory staging: head_kernel staged 20 KB per warp and
+//                    ran 8 warps per SM at 10 % of the HBM peak).  exp_det + quantisation once per element; 128-element
+//                    block totals by two REDUX (20-bit halves of the 40-bit masses) instead of shuffle trees; only the
+//                    one block that holds the target is scanned.
+//  head_cdf_kernel + head_shared_kernel   when MANY draws / targets share one logits row (dimension 0 of `sample`: all
+//                    M rows are the same observation; `sample_batched`: n draws per observation; dimension 0 of
+//                    `log_prob`): the integer CDF, max and log-partition of each distinct row are computed ONCE, then
+//                    one thread per draw does a 13-step binary search (the old path recomputed 5 000 exponentials per draw).
+#pragma once
+#include "small_kernels.cuh"
+
+namespace pfn {
+
+constexpr int HR_THREADS = 128, HR_VEC = 10, HR_MAX_B = HR_THREADS * HR_VEC * 4;  // 5120 buckets
+
+__device__ __forceinline__ int float_ordered(float f) {  // monotone float -> int map (for REDUX max)
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float ordered_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__device__ __forceinline__ unsigned long long warp_scan_u64(unsigned long long v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// sum over the warp of a value < 2^42 that is itself a sum of <= 4 masses <= 2^40: two 32-bit REDUX on its 20-bit halves
+__device__ __forceinline__ unsigned long long warp_sum_q(unsigned long long s) {
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(s & 0xFFFFFull));
+    const unsigned hi = __reduce_add_sync(0xffffffffu, (unsigned)(s >> 20));
+    return ((unsigned long long)hi << 20) + (unsigned long long)lo;
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(HR_THREADS) head_row_kernel(HeadArgs a) {
+    __shared__ int s_max[4];
+    __shared__ unsigned long long s_w[4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B = a.B;
+    const int nvec = B >> 2;  // B % 4 == 0
+    const double kLn2x40 = 40.0 * 0.6931471805599453;
+    for (int64_t r = blockIdx.x; r < a.M; r += gridDim.x) {
+        const float* lg = a.logits + (r / a.group) * a.ld_logits;
+        const float4* lg4 = reinterpret_cast<const float4*>(lg);
+        // element order: warp w owns float4 indices [320 w, 320 w + 320), block k of the warp = indices 320 w + 32 k + lane
+        float v[4 * HR_VEC];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < HR_VEC; ++k) {
+            const int f = warp * (32 * HR_VEC) + k * 32 + lane;
+            float4 x = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+            if (f < nvec) x = __ldg(lg4 + f);
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+            mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        }
+        const int wmx = __reduce_max_sync(0xffffffffu, float_ordered(mx));
+        __syncthreads();  // previous row's readers of s_max / s_w are done
+        if (lane == 0) s_max[warp] = wmx;
+        __syncthreads();
+        const float m = ordered_float(max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3])));
+        // block totals T[k] (uniform across the warp) and the warp total
+        unsigned long long T[HR_VEC], wsum = 0ull;
+#pragma unroll
+        for (int k = 0; k < HR_VEC; ++k) {
+            const int f = warp * (32 * HR_VEC) + k * 32 + lane;
+            unsigned long long s = 0ull;
+            if (f < nvec)
+                s = quantize_q40(exp_det(v[4 * k] - m)) + quantize_q40(exp_det(v[4 * k + 1] - m)) +
+                    quantize_q40(exp_det(v[4 * k + 2] - m)) + quantize_q40(exp_det(v[4 * k + 3] - m));
+            T[k] = warp_sum_q(s);
+            wsum += T[k];
+        }
+        if (lane == 0) s_w[warp] = wsum;
+        __syncthreads();
+        const unsigned long long W0 = s_w[0], W1 = s_w[1], W2 = s_w[2], W3 = s_w[3];
+        const unsigned long long Z = W0 + W1 + W2 + W3;
+
+        if (!SAMPLE) {
+            if (threadIdx.x == 0) {
+                const double logZ = log((double)Z) - kLn2x40;
+                const float yv = a.y[r * a.ld_y];
+                const double logp = bar_logp(lg, B, a.borders, m, logZ, yv);
+                if (a.out_nll) a.out_nll[r] = (float)(-logp);
+                if (a.out_logp) {
+                    float lp = (float)logp;
+                    if (lp == -INFINITY) lp = a.log_eps;
+                    a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+                }
+            }
+            continue;
+        }
+
+        float u;
+        if (a.uniforms) u = a.uniforms[r];
+        else {
+            uint32_t c[4];
+            philox4x32_10(a.seed, a.row0 + (uint64_t)r, a.offset, c);
+            u = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;
+        }
+        const double target = (double)u * (double)Z;
+        // the warp that holds the target: first w whose inclusive total is not below it
+        const unsigned long long c0 = W0, c1 = c0 + W1, c2 = c1 + W2;
+        int wsel = 4;
+        unsigned long long run = 0ull;
+        if (!((double)c0 < target)) { wsel = 0; run = 0ull; }
+        else if (!((double)c1 < target)) { wsel = 1; run = c0; }
+        else if (!((double)c2 < target)) { wsel = 2; run = c1; }
+        else if (!((double)Z < target)) { wsel = 3; run = c2; }
+        if (wsel == 4) {  // unreachable for u < 1 (spec: last bucket, no mass)
+            if (threadIdx.x == 0) {
+                const int idx = B - 1;
+                a.out_theta[r * a.ld_theta] = a.borders[idx];
+                if (a.out_bin) a.out_bin[r] = idx;
+                if (a.out_u) a.out_u[r] = u;
+                if (a.out_logp) {
+                    const double logZ = log((double)Z) - kLn2x40;
+                    float lp = (float)bar_logp(lg, B, a.borders, m, logZ, a.borders[idx]);
+                    if (lp == -INFINITY) lp = a.log_eps;
+                    a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+                }
+            }
+            continue;
+        }
+        if (warp != wsel) continue;
+        // block of the warp that holds the target
+        int ksel = HR_VEC - 1;
+        {
+            unsigned long long c = run;
+            bool found = false;
+#pragma unroll
+            for (int k = 0; k < HR_VEC; ++k) {
+                if (!found) {
+                    if (!((double)(c + T[k]) < target)) { ksel = k; found = true; }
+                    else c += T[k];
+                }
+            }
+            run = c;
+        }
+        // the four masses of this lane in that block (compile-time register indices, one predicated branch taken)
+        unsigned long long q[4] = {0ull, 0ull, 0ull, 0ull};
+        float lv[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < HR_VEC; ++k) {
+            if (k == ksel) {
+                const int f = warp * (32 * HR_VEC) + k * 32 + lane;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    lv[c] = v[4 * k + c];
+                    q[c] = f < nvec ? quantize_q40(exp_det(v[4 * k + c] - m)) : 0ull;
+                }
+            }
+        }
+        const unsigned long long s4 = q[0] + q[1] + q[2] + q[3];
+        const unsigned long long inc = warp_scan_u64(s4, lane) + run;  // inclusive prefix up to this lane's last element
+        const unsigned below = __ballot_sync(0xffffffffu, (double)inc < target);
+        const int lsel = __popc(below);  // first lane whose inclusive prefix is not below the target (< 32 by construction)
+        if (lane == min(lsel, 31)) {
+            unsigned long long Cprev = inc - s4, qsel = 0ull;
+            int j = 3;
+            float lsel_v = lv[3];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                if (j == 3 && c < 3) {
+                    if (!((double)(Cprev + q[c]) < target)) { j = c; }
+                    else Cprev += q[c];
+                }
+            }
+            qsel = q[j];
+            lsel_v = lv[j];
+            const int idx = 4 * (warp * (32 * HR_VEC) + ksel * 32 + lane) + j;
+            double frac = qsel ? (target - (double)Cprev) / (double)qsel : 0.0;
+            frac = fmin(fmax(frac, 0.0), 1.0);
+            const double lo = (double)a.borders[idx], hi = (double)a.borders[idx + 1];
+            const float th = (float)(lo + (hi - lo) * frac);
+            a.out_theta[r * a.ld_theta] = th;
+            if (a.out_bin) a.out_bin[r] = idx;
+            if (a.out_u) a.out_u[r] = u;
+            if (a.out_logp) {
+                const double logZ = log((double)Z) - kLn2x40;
+                (void)lsel_v;
+                float lp = (float)bar_logp(lg, B, a.borders, m, logZ, th);
+                if (lp == -INFINITY) lp = a.log_eps;
+                a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+            }
+        }
+    }
+}
+
+// ---- shared logits rows: integer CDF once per distinct row, then one thread per draw / target ---------------------------
+struct HeadCdf {            // per distinct logits row
+    unsigned long long* cdf;  // [rows][B] inclusive prefix sums of the bucket masses
+    float* row_max;           // [rows]
+    double* logZ;             // [rows]
+};
+
+constexpr int HC_THREADS = 256;
+__global__ void __launch_bounds__(HC_THREADS) head_cdf_kernel(const float* __restrict__ logits, int64_t ld, int B, HeadCdf o) {
+    __shared__ float s_mx[HC_THREADS / 32];
+    __shared__ unsigned long long s_ws[HC_THREADS / 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t row = blockIdx.x;
+    const float* lg = logits + row * ld;
+    const int per = (B + HC_THREADS - 1) / HC_THREADS;  // contiguous buckets per thread
+    const int i0 = min((int)threadIdx.x * per, B), i1 = min(i0 + per, B);
+    float mx = -INFINITY;
+    for (int i = i0; i < i1; ++i) mx = fmaxf(mx, lg[i]);
+    mx = warp_max(mx);
+    if (lane == 0) s_mx[warp] = mx;
+    __syncthreads();
+    float m = s_mx[0];
+#pragma unroll
+    for (int w = 1; w < HC_THREADS / 32; ++w) m = fmaxf(m, s_mx[w]);
+    unsigned long long s = 0ull;
+    for (int i = i0; i < i1; ++i) s += quantize_q40(exp_det(lg[i] - m));
+    const unsigned long long inc = warp_scan_u64(s, lane);
+    if (lane == 31) s_ws[warp] = inc;
+    __syncthreads();
+    unsigned long long before = 0ull, Z = 0ull;
+#pragma unroll
+    for (int w = 0; w < HC_THREADS / 32; ++w) {
+        if (w < warp) before += s_ws[w];
+        Z += s_ws[w];
+    }
+    unsigned long long c = before + inc - s;
+    unsigned long long* out = o.cdf + row * (int64_t)B;
+    for (int i = i0; i < i1; ++i) {
+        c += quantize_q40(exp_det(lg[i] - m));
+        out[i] = c;
+    }
+    if (threadIdx.x == 0) {
+        o.row_max[row] = m;
+        o.logZ[row] = log((double)Z) - 40.0 * 0.6931471805599453;
+    }
+}
+
+// log density of y given the row's max and log partition, reading the one logit it needs from global memory
+__device__ __forceinline__ double bar_logp_shared(const float* __restrict__ lg, int B, const float* __restrict__ borders, float m,
+                                                  double logZ, float y) {
+    return bar_logp(lg, B, borders, m, logZ, y);
+}
+
+template <bool SAMPLE>
+__global__ void __launch_bounds__(256) head_shared_kernel(HeadArgs a, HeadCdf o) {
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= a.M) return;
+    const int B = a.B;
+    const int64_t row = a.ld_logits == 0 ? 0 : r / a.group;
+    const float* lg = a.logits + row * a.ld_logits;
+    const float m = o.row_max[row];
+    const double logZ = o.logZ[row];
+    if (!SAMPLE) {
+        const double logp = bar_logp(lg, B, a.borders, m, logZ, a.y[r * a.ld_y]);
+        if (a.out_nll) a.out_nll[r] = (float)(-logp);
+        if (a.out_logp) {
+            float lp = (float)logp;
+            if (lp == -INFINITY) lp = a.log_eps;
+            a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+        }
+        return;
+    }
+    const unsigned long long* __restrict__ C = o.cdf + row * (int64_t)B;
+    float u;
+    if (a.uniforms) u = a.uniforms[r];
+    else {
+        uint32_t c[4];
+        philox4x32_10(a.seed, a.row0 + (uint64_t)r, a.offset, c);
+        u = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;
+    }
+    const unsigned long long Z = C[B - 1];
+    const double target = (double)u * (double)Z;
+    int lo_i = 0, hi_i = B;  // first i with !(C_i < target)
+    while (lo_i < hi_i) {
+        const int mid = (lo_i + hi_i) >> 1;
+        if ((double)C[mid] < target) lo_i = mid + 1; else hi_i = mid;
+    }
+    int idx = lo_i;
+    unsigned long long Cprev, qsel;
+    if (idx >= B) { idx = B - 1; Cprev = Z; qsel = 0ull; }
+    else { Cprev = idx ? C[idx - 1] : 0ull; qsel = C[idx] - Cprev; }
+    double frac = qsel ? (target - (double)Cprev) / (double)qsel : 0.0;
+    frac = fmin(fmax(frac, 0.0), 1.0);
+    const double lo = (double)a.borders[idx], hi = (double)a.borders[idx + 1];
+    const float th = (float)(lo + (hi - lo) * frac);
+    a.out_theta[r * a.ld_theta] = th;
+    if (a.out_bin) a.out_bin[r] = idx;
+    if (a.out_u) a.out_u[r] = u;
+    if (a.out_logp) {
+        float lp = (float)bar_logp(lg, B, a.borders, m, logZ, th);
+        if (lp == -INFINITY) lp = a.log_eps;
+        a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+    }
+}
+
+}  // namespace pfn

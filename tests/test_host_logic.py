@@ -172,11 +172,20 @@ class _FakePosterior:
     def log_prob(self, theta, x):
         return theta.sum(1)
 
+    _theta_train = torch.zeros(1, 2)
+
+    def sample_batched(self, x, shape, with_log_prob=False):
+        """observation o of this rank's block -> draws (value of x[o, 0], draw index)"""
+        n = shape[0]
+        s = torch.stack([x[:, :1].expand(-1, n), torch.arange(n, dtype=torch.float32).expand(x.shape[0], n)], -1)
+        return (s, s.sum(-1)) if with_log_prob else s
+
 
 def _worker(rank, world, port, q):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
-    from npe_pfn_b200.distributed import gather_rows, log_prob_sharded, reduce_counts, sample_sharded, shard_bounds
+    from npe_pfn_b200.distributed import (gather_rows, log_prob_sharded, reduce_counts, sample_batched_sharded, sample_sharded,
+                                          shard_bounds)
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     try:
         total = 11
@@ -189,6 +198,12 @@ def _worker(rank, world, port, q):
         th = torch.arange(14, dtype=torch.float32).reshape(7, 2)
         ok &= torch.equal(log_prob_sharded(_FakePosterior(), th, None), th.sum(1))
         ok &= reduce_counts(rank + 1, 10) == (sum(range(1, world + 1)), 10 * world)
+        # observations split over the ranks, gathered back in observation order (also with fewer observations than ranks)
+        for num_obs in (5, 1):
+            xs = torch.arange(num_obs, dtype=torch.float32)[:, None].repeat(1, 3) + 100.0
+            sb, sblp = sample_batched_sharded(_FakePosterior(), xs, 4, with_log_prob=True)
+            ok &= sb.shape == (num_obs, 4, 2) and sblp.shape == (num_obs, 4)
+            ok &= torch.equal(sb[:, :, 0], xs[:, :1].expand(-1, 4)) and torch.equal(sblp, sb.sum(-1))
         q.put((rank, bool(ok)))
     finally:
         dist.destroy_process_group()
