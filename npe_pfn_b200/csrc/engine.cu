@@ -26,6 +26,7 @@
 #include "mlp_tc.cuh"
 #endif
 #include "small_kernels.cuh"
+#include "head_kernels.cuh"
 #include "filter_kernels.cuh"
 #include "ensemble_kernels.cuh"
 
@@ -78,6 +79,12 @@ struct pfn_ctx {
     bf16* dech = nullptr;
     float* logits = nullptr;
     // compaction scratch
+    // head: integer CDFs of logits rows that many draws share (head_kernels.cuh)
+    unsigned long long* hd_cdf = nullptr;
+    float* hd_max = nullptr;
+    double* hd_logZ = nullptr;
+    int64_t hd_rows = 0;
+    int head_impl = 1;  // 0 = round-1 warp-per-row kernel (shared-memory staging), 1 = register-resident rows + shared-row CDFs
     unsigned long long* cp_state = nullptr;  // [cp_cap] look-back tile states | 2 ticket words (zeroed per launch)
     int64_t cp_cap = 0;
     // on-device rejection loop (pfn_sample_rejection): joint test matrix / log-probs of one proposal round
@@ -372,14 +379,44 @@ int decode_rows(pfn_ctx* c, const Slot& s, int64_t r0, int64_t n, float* out, in
 }
 
 int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
+    // algorithmic bytes: every distinct logits row once (20 000 B) + the row's scalar inputs / outputs
+    const int64_t distinct = h.ld_logits == 0 ? 1 : ceil_div(h.M, h.group);
+    TimeScope ts(c, st, KC_HEAD, 0.0, (double)distinct * h.B * 4.0 + (double)h.M * 12.0);
+    if (c->head_impl == 1 && h.M >= 2 * distinct && h.M >= 64) {
+        // many draws / targets per logits row: CDF once per distinct row, then one thread per draw
+        if (distinct > c->hd_rows) {
+            PFN_CUDA_OK(cudaStreamSynchronize(st));
+            cudaFree(c->hd_cdf); cudaFree(c->hd_max); cudaFree(c->hd_logZ);
+            c->hd_cdf = nullptr; c->hd_max = nullptr; c->hd_logZ = nullptr; c->hd_rows = 0;
+            const int64_t cap = distinct + 64;
+            PFN_CUDA_OK(cudaMalloc(&c->hd_cdf, (size_t)cap * h.B * 8));
+            PFN_CUDA_OK(cudaMalloc(&c->hd_max, (size_t)cap * 4));
+            PFN_CUDA_OK(cudaMalloc(&c->hd_logZ, (size_t)cap * 8));
+            c->hd_rows = cap;
+        }
+        HeadCdf o{c->hd_cdf, c->hd_max, c->hd_logZ};
+        head_cdf_kernel<<<(unsigned)distinct, HC_THREADS, 0, st>>>(h.logits, h.ld_logits, h.B, o);
+        PFN_LAUNCH_OK(c);
+        const unsigned blocks = (unsigned)ceil_div(h.M, 256);
+        if (sample) head_shared_kernel<true><<<blocks, 256, 0, st>>>(h, o);
+        else head_shared_kernel<false><<<blocks, 256, 0, st>>>(h, o);
+        PFN_LAUNCH_OK(c);
+        return 0;
+    }
+    const bool vec_ok = h.B % 4 == 0 && h.B <= HR_MAX_B && h.ld_logits % 4 == 0 &&
+                        (reinterpret_cast<uintptr_t>(h.logits) & 15) == 0;
+    if (c->head_impl == 1 && vec_ok) {
+        const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * 16);
+        if (sample) head_row_kernel<true><<<blocks, HR_THREADS, 0, st>>>(h);
+        else head_row_kernel<false><<<blocks, HR_THREADS, 0, st>>>(h);
+        PFN_LAUNCH_OK(c);
+        return 0;
+    }
     const size_t smem = (size_t)HEAD_WARPS * h.B * sizeof(float);
     if (smem > 48 * 1024) {  // per device and cheap: set it every time
         if (sample) PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         else PFN_CUDA_OK(cudaFuncSetAttribute(head_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     }
-    // algorithmic bytes: every distinct logits row once (20 000 B) + the row's scalar inputs / outputs
-    const double rows_read = h.ld_logits == 0 ? 1.0 : (double)ceil_div(h.M, h.group);
-    TimeScope ts(c, st, KC_HEAD, 0.0, rows_read * h.B * 4.0 + (double)h.M * 12.0);
     const unsigned blocks = (unsigned)std::min<int64_t>(ceil_div(h.M, HEAD_WARPS), 148 * 8);
     if (sample) head_kernel<true><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
     else head_kernel<false><<<blocks, HEAD_WARPS * 32, smem, st>>>(h);
@@ -470,6 +507,9 @@ int pfn_ctx_destroy(pfn_ctx* c) {
     cudaFree(c->dech);
     cudaFree(c->logits);
     cudaFree(c->cp_state);
+    cudaFree(c->hd_cdf);
+    cudaFree(c->hd_max);
+    cudaFree(c->hd_logZ);
     cudaFree(c->rj_buf);
     cudaFree(c->rj_logp);
     cudaFree(c->flt_ws);
@@ -488,6 +528,7 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_stagger_ns")) { c->attn_stagger_ns = (int)value; return 0; }
     if (!strcmp(key, "attn_lean")) { c->attn_lean = (int)value; return 0; }
     if (!strcmp(key, "mlp_fused")) { c->mlp_fused = (int)value; return 0; }
+    if (!strcmp(key, "head_impl")) { c->head_impl = (int)value; return 0; }
     if (!strcmp(key, "attn_debug")) {
         if (value && !c->attn_dbg) PFN_CUDA_OK(cudaMalloc(&c->attn_dbg, 3 * sizeof(unsigned long long)));
         if (value) PFN_CUDA_OK(cudaMemset(c->attn_dbg, 0, 3 * sizeof(unsigned long long)));
