@@ -268,3 +268,34 @@ def test_reference_tsnpe_rounds_equal_mirror(ref_pkg):
         mir_ts.TabPFN_Based_NPE_PFN = saved
     assert a._theta_train.shape == (36, 2)
     assert torch.equal(a._theta_train, b._theta_train) and torch.equal(a._x_train, b._x_train)
+
+
+def test_reference_uncond_estimator_equals_mirror(ref_pkg, weights):
+    """`TabPFN_Based_Uncond_Estimator` (npe_pfn.py:747-900, experimental in the reference): the mirror's cluster logic
+    (shuffle, dummy x, k-means, multinomial split, per-cluster context, final permutation, mixture log-prob) against the
+    reference's class, both running the REFERENCE's own hot loops over the oracle estimator, same numpy / torch seeds."""
+    import numpy as np
+    pkg, core = ref_pkg
+    from npe_pfn_b200.uncond import TabPFN_Based_Uncond_Estimator as Mirror
+    from oracle.estimator import OracleTabPFNRegressor
+
+    class MirrorOverOracle(Mirror):  # the mirror's own methods around the reference's loops and the oracle model
+        _sample = core.NPE_PFN_Core._sample
+        _autoregressive_log_prob = core.NPE_PFN_Core._autoregressive_log_prob
+
+    g = torch.Generator().manual_seed(3)
+    theta = torch.cat([torch.randn(20, 2, generator=g) * 0.3 + c for c in (-2.0, 2.0)])
+    out = {}
+    for name, cls in (("ref", core.TabPFN_Based_Uncond_Estimator), ("mirror", MirrorOverOracle)):
+        est = cls(num_clusters=2, regressor_init_kwargs={"n_estimators": 1})
+        est._model = OracleTabPFNRegressor(weights=weights)
+        torch.manual_seed(11)
+        np.random.seed(11)
+        est.append_simulations(theta)  # KMeans(random_state=None) draws from numpy's global generator, seeded above
+        s, lp = est.sample((9,), with_log_prob=True)
+        lp2 = est.log_prob(s)
+        out[name] = (est._theta_train.clone(), est.counts.copy(), s, lp, lp2)
+    a, b = out["ref"], out["mirror"]
+    assert torch.equal(a[0], b[0]) and (a[1] == b[1]).all()
+    assert a[2].shape == (9, 2) and torch.equal(a[2], b[2]) and torch.allclose(a[3], b[3], atol=1e-6)
+    assert torch.allclose(a[4], b[4], atol=1e-6) and torch.isfinite(b[4]).all()
