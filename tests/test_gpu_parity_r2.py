@@ -305,3 +305,60 @@ def test_posterior_support_device_loop(engine, mode_kwargs):
     s_h, rate_h = ps.sample((500,), show_progress_bars=False, sampling_batch_size=1000, return_acceptance_rate=True)
     assert s_h.shape == (500, 2) and abs(rate - rate_h) <= 0.5 * max(rate, rate_h) + 0.02
     assert (s.mean(0) - s_h.mean(0)).abs().max() <= 0.35 * s_h.std(0).max()
+
+
+def test_edge_cases_round2(engine, weights):
+    """Empty / minimal inputs through the round-2 entry points: zero and one draw, a one-dimensional theta (the rejection
+    loop is then the shared-logits path only), a one-row context, zero observations, shared-logits head with few draws."""
+    from npe_pfn_b200 import BoxUniform, NPE_PFN_Core
+    from oracle import bar_head
+    g = torch.Generator().manual_seed(12)
+    kw = {"engine": engine, "n_estimators": 1}
+    # d_theta = 1, N = 1 .. 40
+    for N in (1, 2, 40):
+        theta = torch.randn(N, 1, generator=g)
+        x = theta + 0.1 * torch.randn(N, 2, generator=g)
+        box = BoxUniform(-50 * torch.ones(1), 50 * torch.ones(1))
+        post = NPE_PFN_Core(prior=box, regressor_init_kwargs=kw).append_simulations(theta, x)
+        assert post.sample((0,), x[:1]).shape[0] == 0
+        s, lp = post.sample((1,), x[:1], with_log_prob=True)
+        assert s.shape == (1, 1) and lp.shape == (1,) and torch.isfinite(s).all() and torch.isfinite(lp).all()
+        s = post.sample((77,), x[:1], max_sampling_batch_size=10)
+        assert s.shape == (77, 1) and bool(box.support.check(s).all())
+        assert post.log_prob(s, x[:1]).shape == (77,)
+        sb = post.sample_batched(x[:1].repeat(3, 1), (5,))
+        assert sb.shape == (3, 5, 1)
+        assert post.sample_batched(x[:0], (4,)).shape[0] == 0
+    # head: shared logits row with M below / above the switch to the CDF path, grouped rows, against the oracle
+    B = weights.cfg.num_buckets
+    engine.prefill(2, torch.randn(30, 2, generator=g), torch.randn(30, generator=g))
+    borders = engine.slot_export(2)["borders"].cpu()
+    logits = torch.randn(3, B, generator=g) * 2
+    for M, group in ((3, 1), (6, 2), (63, 21), (192, 64), (3000, 1000)):
+        u = torch.rand(M, generator=g)
+        th, bins, lp = engine.head_sample(2, logits, M=M, group=group, uniforms=u, return_bins=True, with_log_prob=True)
+        rows = torch.arange(M) // group
+        th_ref, idx_ref, _ = bar_head.sample(logits[rows].contiguous(), borders, uniforms=u)
+        assert torch.equal(bins.cpu(), idx_ref) and torch.equal(th.cpu(), th_ref), (M, group)
+        assert torch.allclose(-lp.cpu(), bar_head.nll(logits[rows].contiguous(), borders, th_ref), atol=2e-5, rtol=1e-5)
+    # nll of many targets against ONE logits row (dimension 0 of log_prob)
+    y = torch.linspace(float(borders[0]) - 1, float(borders[-1]) + 1, 500)
+    nll = engine.head_nll(2, logits[:1], y).cpu()
+    assert torch.allclose(nll, bar_head.nll(logits[:1].expand(500, B).contiguous(), borders, y), atol=2e-5, rtol=1e-5)
+    # old head kernel (head_impl = 0) gives the same bits as the new ones
+    u = torch.rand(300, generator=g)
+    lg = torch.randn(300, B, generator=g)
+    a = engine.head_sample(2, lg, uniforms=u, return_bins=True)
+    engine.set_option("head_impl", 0)
+    try:
+        b = engine.head_sample(2, lg, uniforms=u, return_bins=True)
+    finally:
+        engine.set_option("head_impl", 1)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    # uniform box proposals: inside the box, reproducible, different rows differ
+    lo, hi = torch.tensor([-1.0, 2.0, 0.0, -5.0, 1.0]), torch.tensor([1.0, 3.0, 10.0, -4.0, 1.5])
+    c1 = engine.uniform_box(lo, hi, 1000, seed=9, row0=5)
+    c2 = engine.uniform_box(lo, hi, 1000, seed=9, row0=5)
+    assert torch.equal(c1, c2) and bool(((c1 >= lo.cuda()) & (c1 <= hi.cuda())).all()) and not torch.equal(c1[0], c1[1])
+    assert torch.equal(engine.uniform_box(lo, hi, 10, seed=9, row0=15), c1[10:20])
+    assert (c1.mean(0).cpu() - (lo + hi) / 2).abs().max() < 0.4
