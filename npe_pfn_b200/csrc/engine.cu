@@ -64,6 +64,8 @@ struct pfn_ctx {
     Offsets off;
     float* wf = nullptr;  // fp32 blob
     bf16* wb = nullptr;   // bf16 copy of the blob
+    bf16* wb_fqkv = nullptr;  // [L][576][192] feature-attention [Wq; Wk; Wv] in head-pair-major order (gemm_tc.cuh EPI_FEATURE_ATTN)
+    int feat_fused = 1;       // 1: QKV projection + attention between features in one kernel (T <= 16, tcgen05 GEMMs)
     std::vector<Slot> slots;
     // workspace (token capacity `cap_tok`)
     int64_t cap_tok = 0;
@@ -267,10 +269,19 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
         const int64_t t0 = r0 * T, ntok = nr * T;
         GemmArgs g{};
         g.ln_eps = c->cfg.ln_eps;
-        g.A = c->xb + t0 * kE; g.lda = kE; g.W = wb + o.feat_wqkv + (size_t)l * 3 * kE * kE; g.M = ntok; g.N = 3 * kE; g.K = kE;
-        g.Cb = c->qkv_s; g.ldcb = 3 * kE;
-        if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
+#ifdef PFN_WITH_ATTN_TC
+        if (c->gemm_impl == 1 && c->feat_fused && T <= 16) {
+            // QKV projection + attention between the T tokens of each row in ONE kernel: qkv never reaches HBM
+            TimeScope ts(c, st, KC_GEMM, 2.0 * (double)ntok * 3 * kE * kE + 4.0 * (double)nr * T * T * kE);
+            PFN_CUDA_OK(launch_qkv_feature_attn_tc(c->xb + t0 * kE, c->wb_fqkv + (size_t)l * 3 * kE * kE, nr, T, c->ob + t0 * kE,
+                                                   c->num_sms, st));
+            c->launches++;
+        } else
+#endif
         {
+            g.A = c->xb + t0 * kE; g.lda = kE; g.W = wb + o.feat_wqkv + (size_t)l * 3 * kE * kE; g.M = ntok; g.N = 3 * kE; g.K = kE;
+            g.Cb = c->qkv_s; g.ldcb = 3 * kE;
+            if (int rc = gemm<EPI_BF16>(c, g, st)) return rc;
             TimeScope ts(c, st, KC_OTHER, 4.0 * (double)nr * T * T * kE);
             if (T <= 16) {
                 feature_attn_mma_kernel<<<(unsigned)ceil_div(nr * kHeads, FAM_WARPS), FAM_WARPS * 32, 0, st>>>(
@@ -482,6 +493,17 @@ int pfn_ctx_create(const pfn_model_config* cfg, const float* weights, size_t n_f
     scale_item_q_kernel<<<(unsigned)ceil_div((int64_t)kE * kE * cfg->nlayers, 256), 256, 0, st>>>(
         c->wf, c->wb, (int64_t)c->off.item_wqkv, cfg->nlayers, kItemScaleLog2);
     PFN_LAUNCH_OK(c);
+    {
+        // head-pair-major copy of every layer's feature-attention projection: chunk hp = rows [q | k | v] of heads 2hp, 2hp + 1
+        const size_t per_layer = (size_t)3 * kE * kE;
+        PFN_CUDA_OK(cudaMalloc(&c->wb_fqkv, (size_t)cfg->nlayers * per_layer * sizeof(bf16)));
+        for (int l = 0; l < cfg->nlayers; ++l)
+            for (int hp = 0; hp < kHeads / 2; ++hp)
+                for (int part = 0; part < 3; ++part)  // q, k, v
+                    PFN_CUDA_OK(cudaMemcpyAsync(c->wb_fqkv + l * per_layer + ((size_t)hp * 3 + part) * 2 * kDh * kE,
+                                                c->wb + c->off.feat_wqkv + l * per_layer + ((size_t)part * kE + (size_t)hp * 2 * kDh) * kE,
+                                                (size_t)2 * kDh * kE * sizeof(bf16), cudaMemcpyDeviceToDevice, st));
+    }
     c->slots.resize(cfg->max_slots);
     for (auto& s : c->slots) {
         PFN_CUDA_OK(cudaMalloc(&s.enc, kEncFloats * 4));
@@ -503,6 +525,7 @@ int pfn_ctx_destroy(pfn_ctx* c) {
     }
     cudaFree(c->wf);
     cudaFree(c->wb);
+    cudaFree(c->wb_fqkv);
     cudaFree(c->ws);
     cudaFree(c->dech);
     cudaFree(c->logits);
@@ -529,6 +552,7 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_lean")) { c->attn_lean = (int)value; return 0; }
     if (!strcmp(key, "mlp_fused")) { c->mlp_fused = (int)value; return 0; }
     if (!strcmp(key, "head_impl")) { c->head_impl = (int)value; return 0; }
+    if (!strcmp(key, "feat_fused")) { c->feat_fused = (int)value; return 0; }
     if (!strcmp(key, "attn_debug")) {
         if (value && !c->attn_dbg) PFN_CUDA_OK(cudaMalloc(&c->attn_dbg, 3 * sizeof(unsigned long long)));
         if (value) PFN_CUDA_OK(cudaMemset(c->attn_dbg, 0, 3 * sizeof(unsigned long long)));

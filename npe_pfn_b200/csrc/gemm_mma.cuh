@@ -8,7 +8,8 @@
 
 namespace pfn {
 
-enum GemmEpi { EPI_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESID_LN = 2, EPI_BIAS_SCALE_F32 = 3 };
+enum GemmEpi { EPI_BF16 = 0, EPI_BIAS_GELU_BF16 = 1, EPI_RESID_LN = 2, EPI_BIAS_SCALE_F32 = 3,
+               EPI_FEATURE_ATTN = 4 /* gemm_tc.cuh only: QKV projection + attention between features in the epilogue */ };
 
 struct GemmArgs {
     const bf16* A;

@@ -5,6 +5,12 @@
 //   EPI_BIAS_GELU_BF16  -> gelu(acc + bias) as bf16          (MLP up-projection, decoder hidden)
 //   EPI_RESID_LN        -> LayerNorm(acc + residual), fp32 residual stream in/out + bf16 copy (N == 192)
 //   EPI_BIAS_SCALE_F32  -> (acc + bias) * scale as fp32      (decoder logits / temperature)
+//   EPI_FEATURE_ATTN    -> the feature-attention QKV projection FUSED with the attention between the T <= 16 tokens of a
+//                          row: W is the head-pair-major permutation of [Wq; Wk; Wv] (chunk hp = q, k, v of heads 2hp and
+//                          2hp+1), an M tile holds whole rows (floor(128 / T) rows), the epilogue rounds the accumulator
+//                          to bf16 into shared memory and runs the row-wise attention there with warp-level mma.sync
+//                          (the arithmetic of feature_attn_mma_kernel, bit for bit); only the attention output [tokens,
+//                          192] goes back to HBM - the [tokens, 576] qkv round trip (2.3 KB per token and layer) is gone.
 //
 // Persistent, warp-specialised, one CTA per SM (320 threads):
 //   warps 0-3 / 4-7  two epilogue warpgroups, alternating over the CTA's tiles (thread = output row = TMEM lane):
@@ -29,6 +35,15 @@ constexpr int GT_STAGE_BYTES = GT_A_BYTES + GT_B_BYTES;
 constexpr int GT_EPI_WARPS = 8;
 constexpr int GT_STAGING_BYTES = 8192;          // per epilogue warp: two 4 KB sub-tile buffers
 constexpr int GT_SMEM_BYTES = 1024 + GT_STAGES * GT_STAGE_BYTES + GT_EPI_WARPS * GT_STAGING_BYTES + 512;
+// EPI_FEATURE_ATTN: 3 ring stages; per epilogue warpgroup a [128 tokens][192 bf16] q|k|v tile with 400-byte rows (16-byte
+// aligned, 100 words = 4 mod 32 banks: the 8 rows x 4 columns of an mma fragment load hit 32 different banks)
+constexpr int GT_FA_STAGES = 3, GT_FA_ROW_BYTES = 400, GT_FA_WG_BYTES = GT_BM * GT_FA_ROW_BYTES;
+constexpr int GT_FA_SMEM_BYTES = 1024 + GT_FA_STAGES * GT_STAGE_BYTES + 2 * GT_FA_WG_BYTES + 512;
+template <int EPI> struct GtCfg {
+    static constexpr int stages = EPI == EPI_FEATURE_ATTN ? GT_FA_STAGES : GT_STAGES;
+    static constexpr int staging_bytes = EPI == EPI_FEATURE_ATTN ? 2 * GT_FA_WG_BYTES : GT_EPI_WARPS * GT_STAGING_BYTES;
+    static constexpr int smem_bytes = EPI == EPI_FEATURE_ATTN ? GT_FA_SMEM_BYTES : GT_SMEM_BYTES;
+};
 constexpr int GT_TMEM_COLS = 512, GT_ACC_STRIDE = 256;
 
 struct GemmTcArgs {
@@ -42,6 +57,10 @@ struct GemmTcArgs {
     float scale, ln_eps;
     int n_chunks;
     int64_t tiles;
+    // EPI_FEATURE_ATTN: tokens per row, rows per M tile, total rows, output [rows * T, 192] bf16 (row stride 192)
+    int T, rows_per_tile;
+    int64_t R;
+    int64_t m_stride;  // first A row of M tile i = i * m_stride (GT_BM for every other epilogue)
 };
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
@@ -244,6 +263,112 @@ __device__ __forceinline__ void gemm_tc_epilogue(const GemmTcArgs& p, const EpiM
     }
 }
 
+// EPI_FEATURE_ATTN, one epilogue warpgroup (4 warps, 128 threads = 128 tokens of the M tile), one head pair `hp`.
+// `buf` = the warpgroup's [128][GT_FA_ROW_BYTES] tile, `bar_id` = its named barrier, `acc_empty` = the accumulator's
+// release barrier (arrived as soon as the accumulator has been copied out, so the next tile's MMAs overlap the attention).
+__device__ __forceinline__ void gemm_tc_feature_attn(const GemmTcArgs& p, uint32_t tacc, uint8_t* buf, int bar_id, uint32_t acc_empty,
+                                                     int64_t m_blk, int hp, int wq, int lane) {
+    // 1. accumulator row (q | k | v of two heads, 192 fp32) -> bf16 -> this token's row of the tile
+    uint8_t* myrow = buf + (size_t)(wq * 32 + lane) * GT_FA_ROW_BYTES;
+#pragma unroll 1
+    for (int c = 0; c < GT_BN / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tacc + c * 32, v);
+        tmem_wait_ld();
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 w;
+            w.x = pack_bf16x2(__uint_as_float(v[8 * q + 0]), __uint_as_float(v[8 * q + 1]));
+            w.y = pack_bf16x2(__uint_as_float(v[8 * q + 2]), __uint_as_float(v[8 * q + 3]));
+            w.z = pack_bf16x2(__uint_as_float(v[8 * q + 4]), __uint_as_float(v[8 * q + 5]));
+            w.w = pack_bf16x2(__uint_as_float(v[8 * q + 6]), __uint_as_float(v[8 * q + 7]));
+            *reinterpret_cast<uint4*>(myrow + c * 64 + q * 16) = w;
+        }
+    }
+    tc_fence_before();
+    mbar_arrive(acc_empty);  // the tensor pipe may refill this accumulator now
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");
+    // 2. attention between the T tokens of each row, one warp per (row, head): the whole T x T problem is one 16 x 16 tile
+    //    (S = Q K^T: 2 n-tiles x 2 k-steps of m16n8k16; O = P V: 4 n-tiles x 1 k-step), as feature_attn_mma_kernel does
+    const int T = p.T, G = p.rows_per_tile;
+    const int g = lane >> 2, tq = lane & 3;
+    constexpr int ts = GT_FA_ROW_BYTES / 2;  // token stride in bf16 elements
+    auto ld32 = [](const bf16* ptr) { return *reinterpret_cast<const uint32_t*>(ptr); };
+    for (int pair = wq; pair < 2 * G; pair += 4) {
+        const int rl = pair >> 1, hh = pair & 1;
+        const int64_t r = m_blk * G + rl;
+        if (r >= p.R) break;  // warp-uniform (pairs grow with the row)
+        const bf16* base = reinterpret_cast<const bf16*>(buf) + (size_t)(rl * T) * ts + hh * kDh;
+        const int q0 = min(g, T - 1), q1 = min(g + 8, T - 1);
+        float s[2][4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) s[n][0] = s[n][1] = s[n][2] = s[n][3] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk) {
+            uint32_t a[4];
+            a[0] = ld32(base + q0 * ts + 16 * kk + 2 * tq);
+            a[1] = ld32(base + q1 * ts + 16 * kk + 2 * tq);
+            a[2] = ld32(base + q0 * ts + 16 * kk + 8 + 2 * tq);
+            a[3] = ld32(base + q1 * ts + 16 * kk + 8 + 2 * tq);
+#pragma unroll
+            for (int n = 0; n < 2; ++n) {
+                const int key = min(8 * n + g, T - 1);
+                const uint32_t b0 = ld32(base + key * ts + 64 + 16 * kk + 2 * tq);
+                const uint32_t b1 = ld32(base + key * ts + 64 + 16 * kk + 8 + 2 * tq);
+                mma_bf16_16816(s[n], a, b0, b1);
+            }
+        }
+        const float sc = 0.17677669529663687f * 1.4426950408889634f;
+        float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const int key = 8 * n + 2 * tq;
+            if (key >= T) { s[n][0] = -INFINITY; s[n][2] = -INFINITY; }
+            if (key + 1 >= T) { s[n][1] = -INFINITY; s[n][3] = -INFINITY; }
+            mx[0] = fmaxf(mx[0], fmaxf(s[n][0], s[n][1]));
+            mx[1] = fmaxf(mx[1], fmaxf(s[n][2], s[n][3]));
+        }
+        float l[2] = {0.f, 0.f};
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 1));
+            mx[i] = fmaxf(mx[i], __shfl_xor_sync(0xffffffffu, mx[i], 2));
+            mx[i] *= sc;
+        }
+        uint32_t pa[4];
+#pragma unroll
+        for (int n = 0; n < 2; ++n) {
+            const float p0 = exp2f(fmaf(s[n][0], sc, -mx[0])), p1 = exp2f(fmaf(s[n][1], sc, -mx[0]));
+            const float p2 = exp2f(fmaf(s[n][2], sc, -mx[1])), p3 = exp2f(fmaf(s[n][3], sc, -mx[1]));
+            l[0] += p0 + p1;
+            l[1] += p2 + p3;
+            pa[2 * n + 0] = pack_bf16x2(p0, p1);
+            pa[2 * n + 1] = pack_bf16x2(p2, p3);
+        }
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            l[i] += __shfl_xor_sync(0xffffffffu, l[i], 1);
+            l[i] += __shfl_xor_sync(0xffffffffu, l[i], 2);
+        }
+        const unsigned short* vb = reinterpret_cast<const unsigned short*>(base + 128);
+        const int k0 = min(2 * tq, T - 1), k1 = min(2 * tq + 1, T - 1), k2 = min(2 * tq + 8, T - 1), k3 = min(2 * tq + 9, T - 1);
+        const float inv0 = 1.0f / l[0], inv1 = 1.0f / l[1];
+        bf16* out = p.Cb + (r * T) * kE + (2 * hp + hh) * kDh;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int dh = 8 * j + g;
+            const uint32_t b0 = (uint32_t)vb[k0 * ts + dh] | ((uint32_t)vb[k1 * ts + dh] << 16);
+            const uint32_t b1 = (uint32_t)vb[k2 * ts + dh] | ((uint32_t)vb[k3 * ts + dh] << 16);
+            float o[4] = {0.f, 0.f, 0.f, 0.f};
+            mma_bf16_16816(o, pa, b0, b1);
+            const int col = 8 * j + 2 * tq;
+            if (g < T) *reinterpret_cast<uint32_t*>(out + (int64_t)g * kE + col) = pack_bf16x2(o[0] * inv0, o[1] * inv0);
+            if (g + 8 < T) *reinterpret_cast<uint32_t*>(out + (int64_t)(g + 8) * kE + col) = pack_bf16x2(o[2] * inv1, o[3] * inv1);
+        }
+    }
+    asm volatile("bar.sync %0, 128;" ::"r"(bar_id) : "memory");  // everyone is done reading before the tile is overwritten
+}
+
 template <int EPI>
 __global__ void __launch_bounds__(GT_THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -251,11 +376,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t gt_smem_raw[];
     const uint32_t raw = smem_u32(gt_smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
-    const uint32_t staging = base + GT_STAGES * GT_STAGE_BYTES;                 // 8 epilogue warps x 8 KB
-    const uint32_t bars = staging + GT_EPI_WARPS * GT_STAGING_BYTES;
-    const uint32_t bar_full = bars;                      // [GT_STAGES]
-    const uint32_t bar_empty = bars + 8 * GT_STAGES;     // [GT_STAGES]
-    const uint32_t bar_acc_full = bars + 16 * GT_STAGES;   // [2]
+    constexpr int NST = GtCfg<EPI>::stages;
+    const uint32_t staging = base + NST * GT_STAGE_BYTES;                       // 8 epilogue warps x 8 KB (FEATURE_ATTN: 2 x 50 KB)
+    const uint32_t bars = staging + GtCfg<EPI>::staging_bytes;
+    const uint32_t bar_full = bars;                      // [NST]
+    const uint32_t bar_empty = bars + 8 * NST;           // [NST]
+    const uint32_t bar_acc_full = bars + 16 * NST;         // [2]
     const uint32_t bar_acc_empty = bar_acc_full + 16;      // [2]
     const uint32_t bar_resid = bar_acc_full + 32;          // [GT_EPI_WARPS][2] residual sub-tiles landed
     const uint32_t tmem_slot = bar_resid + 16 * GT_EPI_WARPS;
@@ -264,7 +390,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int kblocks = p.K / GT_BK;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < GT_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(bar_full + 8 * s, 1);
             mbar_init(bar_empty + 8 * s, 1);
         }
@@ -294,11 +420,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int64_t tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
                 const int m_blk = (int)(tile / p.n_chunks), n_blk = (int)(tile % p.n_chunks);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % GT_STAGES, ph = (it / GT_STAGES) & 1u;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(bar_empty + 8 * s, ph ^ 1u);
                     mbar_expect_tx(bar_full + 8 * s, GT_STAGE_BYTES);
                     const uint32_t dA = base + s * GT_STAGE_BYTES, dB = dA + GT_A_BYTES;
-                    tma_load_2d(dA, &tmA, bar_full + 8 * s, kb * GT_BK, m_blk * GT_BM);
+                    tma_load_2d(dA, &tmA, bar_full + 8 * s, kb * GT_BK, (int)(m_blk * p.m_stride));
                     tma_load_2d(dB, &tmW, bar_full + 8 * s, kb * GT_BK, n_blk * GT_BN);
                 }
             }
@@ -314,7 +440,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
                 const uint32_t d = tmem + b * GT_ACC_STRIDE;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const uint32_t s = it % GT_STAGES, ph = (it / GT_STAGES) & 1u;
+                    const uint32_t s = it % NST, ph = (it / NST) & 1u;
                     mbar_wait(bar_full + 8 * s, ph);
                     tc_fence_after();
                     const uint64_t dA = umma_desc_sw128(base + s * GT_STAGE_BYTES);
@@ -348,9 +474,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             mbar_wait(bar_acc_full + 8 * e, (lt >> 1) & 1u);
             tc_fence_after();
             const uint32_t tacc = tmem + (lane_base << 16) + e * GT_ACC_STRIDE;
-            gemm_tc_epilogue<EPI>(p, mp, tacc, row0, n_blk * GT_BN, stage, rbar, ruse, lane);
-            tc_fence_before();
-            mbar_arrive(bar_acc_empty + 8 * e);
+            if constexpr (EPI == EPI_FEATURE_ATTN) {
+                gemm_tc_feature_attn(p, tacc, gt_smem_raw + (staging - raw) + (size_t)e * GT_FA_WG_BYTES, 1 + (int)e,
+                                     bar_acc_empty + 8 * e, m_blk, n_blk, warp & 3, lane);
+            } else {
+                gemm_tc_epilogue<EPI>(p, mp, tacc, row0, n_blk * GT_BN, stage, rbar, ruse, lane);
+                tc_fence_before();
+                mbar_arrive(bar_acc_empty + 8 * e);
+            }
         }
         if (lane == 0) bulk_wait0();  // all TMA stores of this warp have completed before the CTA exits
     }
@@ -397,10 +528,11 @@ static inline cudaError_t launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStr
     cudaGetDevice(&dev);
     bool& configured = configured_dev[dev & 63];
     if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GT_SMEM_BYTES);
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, GtCfg<EPI>::smem_bytes);
         if (e != cudaSuccess) return e;
         configured = true;
     }
+    static_assert(EPI != EPI_FEATURE_ATTN, "use launch_qkv_feature_attn_tc");
     if (a.K % GT_BK != 0 || (EPI == EPI_RESID_LN && a.N != GT_BN)) return cudaErrorInvalidValue;
     CUtensorMap mA, mW, mCb, mCf;
     if (!make_map2_sw128(&mA, a.A, (uint64_t)a.K, (uint64_t)a.M, (uint64_t)a.lda * 2, GT_BM)) return cudaErrorInvalidValue;
@@ -417,8 +549,38 @@ static inline cudaError_t launch_gemm_tc(const GemmArgs& a, int num_sms, cudaStr
     p.scale = a.scale; p.ln_eps = a.ln_eps;
     p.n_chunks = (a.N + GT_BN - 1) / GT_BN;
     p.tiles = ceil_div(a.M, GT_BM) * p.n_chunks;
+    p.m_stride = GT_BM;
     const unsigned grid = (unsigned)std::min<int64_t>(p.tiles, num_sms);
     gemm_tc_kernel<EPI><<<grid, GT_THREADS, GT_SMEM_BYTES, st>>>(mA, mW, mCb, mCf, p);
+    return cudaGetLastError();
+}
+
+// Fused feature-attention half step: X[rows * T, 192] (bf16, contiguous tokens) x Wperm[576, 192]^T -> attention between the
+// T tokens of every row -> out[rows * T, 192] bf16.  Wperm = head-pair-major permutation of the layer's [Wq; Wk; Wv].
+static inline cudaError_t launch_qkv_feature_attn_tc(const bf16* X, const bf16* Wperm, int64_t rows, int T, bf16* out, int num_sms,
+                                                     cudaStream_t st) {
+    if (T < 1 || T > 16) return cudaErrorInvalidValue;
+    static bool configured_dev[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    bool& configured = configured_dev[dev & 63];
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel<EPI_FEATURE_ATTN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             GT_FA_SMEM_BYTES);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
+    CUtensorMap mA, mW;
+    if (!make_map2_sw128(&mA, X, (uint64_t)kE, (uint64_t)(rows * T), (uint64_t)kE * 2, GT_BM)) return cudaErrorInvalidValue;
+    if (!make_map2_sw128(&mW, Wperm, (uint64_t)kE, (uint64_t)(3 * kE), (uint64_t)kE * 2, GT_BN)) return cudaErrorInvalidValue;
+    GemmTcArgs p{};
+    p.M = rows * T; p.N = 3 * kE; p.K = kE; p.Cb = out; p.ldcb = kE;
+    p.T = T; p.rows_per_tile = GT_BM / T; p.R = rows;
+    p.m_stride = (int64_t)p.rows_per_tile * T;
+    p.n_chunks = 3;
+    p.tiles = ceil_div(rows, p.rows_per_tile) * p.n_chunks;
+    const unsigned grid = (unsigned)std::min<int64_t>(p.tiles, num_sms);
+    gemm_tc_kernel<EPI_FEATURE_ATTN><<<grid, GT_THREADS, GT_FA_SMEM_BYTES, st>>>(mA, mW, mA, mA, p);
     return cudaGetLastError();
 }
 

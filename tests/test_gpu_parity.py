@@ -640,6 +640,28 @@ def test_item_attention_sharp_scores(weights, gain, nlayers):
     eng.close()
 
 
+@pytest.mark.parametrize("F,N,M", [(2, 70, 129), (5, 300, 500), (10, 130, 257), (19, 90, 1000), (29, 64, 77), (30, 40, 1)])
+def test_fused_qkv_feature_attention_bit_equal(engine, F, N, M):
+    """gemm_tc EPI_FEATURE_ATTN (QKV projection + attention between the tokens of a row in one kernel, qkv never written
+    to HBM) against the two-kernel path: the same bf16 q / k / v, the same mma.sync arithmetic -> the SAME bits, for the
+    context pass (K/V cache) and for the test rows (logits), T = 2 .. 16 tokens per row incl. rows that straddle nothing
+    (an M tile holds floor(128 / T) whole rows) and ragged last tiles."""
+    g = torch.Generator().manual_seed(F * 31 + N)
+    Xc = torch.randn(N, F, generator=g)
+    yc = Xc[:, 0] + 0.1 * torch.randn(N, generator=g)
+    Xt = torch.randn(M, F, generator=g)
+    outs, kvs = [], []
+    for fused in (0, 1):
+        engine.set_option("feat_fused", fused)
+        engine.prefill(6, Xc, yc)
+        outs.append(engine.forward_logits(6, Xt))
+        kvs.append(engine.slot_export(6, want_kv=True)["kv"])
+    engine.set_option("feat_fused", 1)
+    assert torch.isfinite(outs[1]).all()
+    assert torch.equal(kvs[0], kvs[1])
+    assert torch.equal(outs[0], outs[1])
+
+
 def test_fused_mlp_kernel_agrees(engine):
     """The fused MLP kernel (mlp_tc.cuh: up-projection, GELU, down-projection, residual, LayerNorm in one launch) against
     the two-kernel tcgen05 path: same bf16 operands and fp32 accumulation, the hidden activation is rounded to bf16 in
