@@ -279,7 +279,15 @@ __device__ __forceinline__ void softmax_exp32_lean(const uint32_t (&s)[32], uint
             p0 = fast_exp2(__uint_as_float(s[2 * i]));
             p1 = fast_exp2(__uint_as_float(s[2 * i + 1]));
         } else {
+            // The clamp at -125 costs 20 FMNMX per tile.  Dropping it (-DPFN_ATTN_LEAN_NOCLAMP) measured +1.5 % (528 vs 519
+            // TFLOP/s, profiles/r2_attn_tc6_experiments.txt) but is only safe while no score lies 512 or more log2 units below
+            // the reference: beyond that the 9 exponent bits kept by `<< 23` wrap to a small POSITIVE value that neither the
+            // sign bits nor the row-sum check see (the sharp-score test reaches such spreads).  Kept.
+#ifndef PFN_ATTN_LEAN_NOCLAMP
             const uint64_t X2 = pk2(fmaxf(__uint_as_float(s[2 * i]), -125.0f), fmaxf(__uint_as_float(s[2 * i + 1]), -125.0f));
+#else
+            const uint64_t X2 = pk2(__uint_as_float(s[2 * i]), __uint_as_float(s[2 * i + 1]));
+#endif
             const uint64_t t2 = fadd2(X2, CM);            // magic + n, n = round(x)
             const uint64_t f2 = fadd2(X2, ffma2(t2, NEG1, CM));  // x - n
             uint64_t q2;
