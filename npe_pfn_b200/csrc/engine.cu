@@ -245,7 +245,7 @@ int forward_rows(pfn_ctx* c, Slot& s, const float* X, int64_t ldx, const float* 
     {
         // algorithmic bytes: F raw features (+ y) in, T tokens of 192 (fp32 + bf16 copy) out per row
         TimeScope ts(c, st, KC_ENCODE, 0.0, (double)R * (4.0 * (s.F + (ctx_rows ? 1 : 0)) + 6.0 * T * kE));
-        encode_kernel<<<(unsigned)ceil_div(R, ENC_ROWS), kE, 0, st>>>(X, ldx, s.F, G, y, R, s.enc, wf + o.enc_x_w,
+        encode_kernel<<<(unsigned)ceil_div(R, ENC_ROWS), ENC_ROWS * ENC_TPR, 0, st>>>(X, ldx, s.F, G, y, R, s.enc, wf + o.enc_x_w,
                                                                      wf + o.enc_y_w, wf + o.enc_y_b, wf + o.pos_emb, c->xf,
                                                                      c->xb);
         PFN_LAUNCH_OK(c);

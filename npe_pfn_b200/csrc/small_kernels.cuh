@@ -107,57 +107,74 @@ __global__ void fit_finalize_kernel(float* __restrict__ enc, int G, const float*
 // cell encoder: rows x F raw features (+ y for context rows) -> token grid [R, T, E] (fp32 + bf16)
 // (oracle/tabpfn_oracle.py::encode_x / encode_y_ctx / encode_y_test)
 // ---------------------------------------------------------------------------------------------
-constexpr int ENC_ROWS = 4;
-__global__ void __launch_bounds__(kE) encode_kernel(const float* __restrict__ X, int64_t ldx, int F, int G,
+// Thread layout (round 2): a block handles ENC_ROWS rows at once, 48 threads per row, each thread FOUR consecutive output
+// features of every token - so the fp32 state goes out as float4 (a warp writes 512 contiguous bytes) and the bf16 copy as
+// 8-byte words instead of the scalar 4- / 2-byte stores of round 1 (0.8 TB/s).  Same fmaf sequence per element: same bits.
+constexpr int ENC_ROWS = 4, ENC_TPR = kE / 4;  // 48 threads per row
+__global__ void __launch_bounds__(ENC_ROWS * ENC_TPR) encode_kernel(const float* __restrict__ X, int64_t ldx, int F, int G,
                                                     const float* __restrict__ y /* null: test rows */,
                                                     int64_t R, const float* __restrict__ enc,
                                                     const float* __restrict__ enc_x_w, const float* __restrict__ enc_y_w,
                                                     const float* __restrict__ enc_y_b, const float* __restrict__ pos_emb,
                                                     float* __restrict__ xf, bf16* __restrict__ xb) {
-    const int e = threadIdx.x;
+    const int rr = threadIdx.x / ENC_TPR, e0 = 4 * (threadIdx.x % ENC_TPR);
     const int T = G + 1;
-    const float4 wx = *reinterpret_cast<const float4*>(enc_x_w + 4 * e);
-    const float2 wy = *reinterpret_cast<const float2*>(enc_y_w + 2 * e);
-    const float by = enc_y_b[e];
-    const float y_mean = enc[kEncY + 0], y_std = enc[kEncY + 1], y_fill = enc[kEncY + 2];
-    for (int rr = 0; rr < ENC_ROWS; ++rr) {
-        const int64_t r = (int64_t)blockIdx.x * ENC_ROWS + rr;
-        if (r >= R) return;
-        const float* xr = X + r * ldx;
-        float* of = xf + r * T * kE;
-        bf16* ob = xb + r * T * kE;
-        for (int g = 0; g < G; ++g) {
-            float f[2], ind[2];
+    const int64_t r = (int64_t)blockIdx.x * ENC_ROWS + rr;
+    if (r >= R) return;
+    float4 wx[4];
+    float2 wy[4];
+    float by[4];
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-                const int c = 2 * g + j;
-                float v = c < F ? xr[c] : 0.f;
-                float id = 0.f;
-                if (isnan(v)) id = -2.f;
-                else if (isinf(v)) id = v > 0.f ? 2.f : 4.f;
-                const float mean = enc[kEncMean + c], sd = enc[kEncStd + c];
-                const float filled = isfinite(v) ? v : mean;
-                float xn = (filled - mean) / (sd + 1e-16f);
-                if (sd == 0.f) xn = 0.f;
-                xn = fminf(fmaxf(xn, -100.f), 100.f);
-                f[j] = xn * enc[kEncScale + g];
-                ind[j] = id;
-            }
-            float v = f[0] * wx.x;
-            v = fmaf(f[1], wx.y, v);
-            v = fmaf(ind[0], wx.z, v);
-            v = fmaf(ind[1], wx.w, v);
-            v += pos_emb[g * kE + e];
-            of[g * kE + e] = v;
-            ob[g * kE + e] = __float2bfloat16_rn(v);
-        }
-        float y0, y1;
-        if (y) { y0 = (y[r] - y_mean) / y_std; y1 = 0.f; }
-        else   { y0 = y_fill; y1 = -2.f; }
-        float v = fmaf(y1, wy.y, y0 * wy.x) + by;
-        of[G * kE + e] = v;
-        ob[G * kE + e] = __float2bfloat16_rn(v);
+    for (int i = 0; i < 4; ++i) {
+        wx[i] = *reinterpret_cast<const float4*>(enc_x_w + 4 * (e0 + i));
+        wy[i] = *reinterpret_cast<const float2*>(enc_y_w + 2 * (e0 + i));
+        by[i] = enc_y_b[e0 + i];
     }
+    const float y_mean = enc[kEncY + 0], y_std = enc[kEncY + 1], y_fill = enc[kEncY + 2];
+    const float* xr = X + r * ldx;
+    float* of = xf + r * T * kE + e0;
+    bf16* ob = xb + r * T * kE + e0;
+    auto store = [&](int tok, const float (&v)[4]) {
+        *reinterpret_cast<float4*>(of + tok * kE) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<uint2*>(ob + tok * kE) = make_uint2(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]));
+    };
+    for (int g = 0; g < G; ++g) {
+        float f[2], ind[2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int c = 2 * g + j;
+            float v = c < F ? xr[c] : 0.f;
+            float id = 0.f;
+            if (isnan(v)) id = -2.f;
+            else if (isinf(v)) id = v > 0.f ? 2.f : 4.f;
+            const float mean = enc[kEncMean + c], sd = enc[kEncStd + c];
+            const float filled = isfinite(v) ? v : mean;
+            float xn = (filled - mean) / (sd + 1e-16f);
+            if (sd == 0.f) xn = 0.f;
+            xn = fminf(fmaxf(xn, -100.f), 100.f);
+            f[j] = xn * enc[kEncScale + g];
+            ind[j] = id;
+        }
+        const float4 pe = *reinterpret_cast<const float4*>(pos_emb + g * kE + e0);
+        const float pev[4] = {pe.x, pe.y, pe.z, pe.w};
+        float out[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float v = f[0] * wx[i].x;
+            v = fmaf(f[1], wx[i].y, v);
+            v = fmaf(ind[0], wx[i].z, v);
+            v = fmaf(ind[1], wx[i].w, v);
+            out[i] = v + pev[i];
+        }
+        store(g, out);
+    }
+    float y0, y1;
+    if (y) { y0 = (y[r] - y_mean) / y_std; y1 = 0.f; }
+    else   { y0 = y_fill; y1 = -2.f; }
+    float out[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) out[i] = fmaf(y1, wy[i].y, y0 * wy[i].x) + by[i];
+    store(G, out);
 }
 
 // ---------------------------------------------------------------------------------------------
