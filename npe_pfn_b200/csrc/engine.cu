@@ -553,6 +553,15 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "mlp_fused")) { c->mlp_fused = (int)value; return 0; }
     if (!strcmp(key, "head_impl")) { c->head_impl = (int)value; return 0; }
     if (!strcmp(key, "feat_fused")) { c->feat_fused = (int)value; return 0; }
+    if (!strcmp(key, "dec_rows")) {  // rows per decoder + head pass (logits workspace = dec_rows x num_buckets fp32)
+        PFN_REQUIRE(value >= 128 && value <= (1 << 20), "dec_rows out of range");
+        PFN_CUDA_OK(cudaSetDevice(c->device));
+        PFN_CUDA_OK(cudaDeviceSynchronize());
+        cudaFree(c->dech); cudaFree(c->logits);
+        c->dech = nullptr; c->logits = nullptr;
+        c->dec_rows = (int)value;
+        return 0;
+    }
     if (!strcmp(key, "attn_debug")) {
         if (value && !c->attn_dbg) PFN_CUDA_OK(cudaMalloc(&c->attn_dbg, 3 * sizeof(unsigned long long)));
         if (value) PFN_CUDA_OK(cudaMemset(c->attn_dbg, 0, 3 * sizeof(unsigned long long)));
