@@ -362,3 +362,38 @@ def test_edge_cases_round2(engine, weights):
     assert torch.equal(c1, c2) and bool(((c1 >= lo.cuda()) & (c1 <= hi.cuda())).all()) and not torch.equal(c1[0], c1[1])
     assert torch.equal(engine.uniform_box(lo, hi, 10, seed=9, row0=15), c1[10:20])
     assert (c1.mean(0).cpu() - (lo + hi) / 2).abs().max() < 0.4
+
+
+def test_estimator_objects_own_their_fit(engine):
+    """Two estimator objects on the same engine slot: each keeps answering from ITS fit - the slot is tagged
+    with the object that built it and rebuilt from the stored fit data when someone else used it in between.  Same for
+    the classifiers behind two DensityRatioWrappers, which share one engine."""
+    import warnings
+    from npe_pfn_b200.estimator import B200TabPFNClassifier, B200TabPFNRegressor
+    g = torch.Generator().manual_seed(91)
+    Xa, Xb = torch.randn(50, 3, generator=g), torch.randn(70, 3, generator=g) + 1.0
+    ya, yb = Xa[:, 0] + 0.1 * torch.randn(50, generator=g), -Xb[:, 1] + 0.1 * torch.randn(70, generator=g)
+    Xt = torch.randn(20, 3, generator=g)
+    a = B200TabPFNRegressor(engine=engine, slot=11, n_estimators=1).fit(Xa, ya)
+    ref_a = a.predict(Xt)["logits"].clone()
+    b = B200TabPFNRegressor(engine=engine, slot=11, n_estimators=1).fit(Xb, yb)
+    ref_b = b.predict(Xt)["logits"].clone()
+    assert not torch.equal(ref_a, ref_b)
+    assert torch.equal(a.predict(Xt)["logits"], ref_a)  # a's slot was overwritten by b: rebuilt, not silently b's
+    assert torch.equal(b.predict(Xt)["logits"], ref_b)
+    crit = a.predict(Xt)["criterion"]
+    assert torch.isfinite(crit(a.predict(Xt)["logits"], torch.zeros(20))).all()
+    Xc = torch.cat([torch.rand(40, 2, generator=g) * 4 - 2, torch.randn(40, 2, generator=g) * 0.5])
+    yc = torch.cat([torch.zeros(40), torch.ones(40)])
+    c1 = B200TabPFNClassifier(n_estimators=1).fit(Xc, yc)
+    p1 = c1.predict_proba(Xt[:, :2])
+    c2 = B200TabPFNClassifier(n_estimators=1).fit(Xc.flip(0) * 0.5, yc.flip(0))
+    p2 = c2.predict_proba(Xt[:, :2])
+    assert abs(p1 - p2).max() > 1e-4
+    assert (c1.predict_proba(Xt[:, :2]) == p1).all() and (c2.predict_proba(Xt[:, :2]) == p2).all()
+    # keyword handling: device strings, upstream runtime kwargs accepted, unknown kwargs reported
+    B200TabPFNRegressor(engine=engine, n_estimators=1, device="cuda", fit_mode="fit_preprocessors")
+    with pytest.warns(UserWarning, match="ignoring unsupported"):
+        B200TabPFNRegressor(engine=engine, n_estimators=1, definitely_not_a_kwarg=3)
+    with pytest.raises(ValueError):
+        B200TabPFNRegressor(n_estimators=1, device="cpu").engine
