@@ -29,7 +29,14 @@ namespace pfn {
 #ifndef PFN_ATTN_CTAS
 #define PFN_ATTN_CTAS 3  // resident CTAs per SM the kernel is compiled for
 #endif
-constexpr int TC_BM = 128, TC_BN = PFN_ATTN_BN, TC_STAGES = TC_BN == 64 ? 7 : 8, TC_THREADS = 192;
+// PFN_ATTN_WG256 (experiment, round 2): CTA of two warpgroups, warps 4-7 (TMA, MMA, two idle) give registers back with
+// setmaxnreg so that the softmax warpgroup runs with 120 instead of 96 registers (the pool is per CTA: 128 x 120 + 128 x 40 = 256 x 80) at the same 3 CTAs per SM
+#ifdef PFN_ATTN_WG256
+constexpr int TC_THREADS = 256;
+#else
+constexpr int TC_THREADS = 192;
+#endif
+constexpr int TC_BM = 128, TC_BN = PFN_ATTN_BN, TC_STAGES = TC_BN == 64 ? 7 : 8;
 static_assert(TC_BN == 64 || TC_BN == 32, "key tile must be 32 or 64");
 constexpr int TC_Q_BYTES = TC_BM * kDh * 2;           // 8 KB: 128 rows x 64 B
 constexpr int TC_TILE_BYTES = TC_BN * kDh * 2;        // 4 KB: 64 keys x 64 B
@@ -382,6 +389,14 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
     tc_fence_after();
     const uint32_t tmem = tmem_slot_ptr[0];     // S/P double buffer
     const uint32_t tmem_o = tmem_slot_ptr[1];   // O accumulator
+#ifdef PFN_ATTN_WG256
+#define PFN_WG_DEC() asm volatile("setmaxnreg.dec.sync.aligned.u32 40;")
+#define PFN_WG_INC() asm volatile("setmaxnreg.inc.sync.aligned.u32 120;")
+    if (warp >= 4) PFN_WG_DEC();  // the whole helper warpgroup executes ONE setmaxnreg (it is warpgroup-aligned)
+#else
+#define PFN_WG_DEC()
+#define PFN_WG_INC()
+#endif
 
     if (p.stagger_ns) {  // de-phase the CTAs that share an SM (they would otherwise run their tiles in lockstep)
         const uint32_t slot = blockIdx.x / p.num_sms;
@@ -463,7 +478,8 @@ attn_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ 
                 tc_commit(bar_o);
             }
         }
-    } else {
+    } else if (warp < 4) {
+        PFN_WG_INC();
         // ================= softmax warps: thread = query row = TMEM lane =================
         const uint32_t trow = tmem + ((uint32_t)(warp * 32) << 16);
         const uint32_t orow = tmem_o + ((uint32_t)(warp * 32) << 16);
