@@ -392,7 +392,7 @@ def main():
     try:  # DRAM bytes per launch of THIS build's attention kernel, from the committed ncu capture (tools/ncu_capture.sh)
         tr = json.load(open(os.path.join(ROOT, "profiles", "r2_attn_traffic.json")))
         from npe_pfn_b200 import build as _b
-        if tr.get("srchash") == _b._source_hash():
+        if tr.get("srchash") == _b.files_hash(_b.ATTN_KERNEL_FILES):
             traffic = tr["dram_bytes_per_launch"] * min(S, 37888) / tr["rows_per_launch"]
     except Exception:
         pass
@@ -407,7 +407,7 @@ def main():
                 "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                 "traffic": traffic,
                 "traffic_note": "ncu dram__bytes_read+write per launch of this build (profiles/r2_attn_traffic.json), scaled to "
-                                "this run's rows per launch; null when no capture of the current sources is committed",
+                                "this run's rows per launch; null when the attention kernel's sources differ from the profiled ones",
                 "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                                if peaks else "fallback 1.4 PFLOP/s sustained",
                 "launches": a_cnt, "avg_launch_ms": a_ms / max(a_cnt, 1),

@@ -39,6 +39,22 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
+def files_hash(names) -> str:
+    """Hash of the named files under csrc/ (+ the nvcc flags): identifies the build of ONE kernel, e.g. the item-attention
+    kernel whose ncu DRAM traffic bench.py reports only while the kernel's sources are the profiled ones."""
+    import hashlib
+    h = hashlib.sha256()
+    for n in sorted(names):
+        h.update(n.encode())
+        with open(os.path.join(CSRC, n), "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+#: sources that define the item-attention kernel of test rows (roofline.traffic in bench.py)
+ATTN_KERNEL_FILES = ["attn_tc.cuh", "attn_mma.cuh", "common.cuh"]
+
 HASH_PATH = LIB_PATH + ".srchash"
 
 

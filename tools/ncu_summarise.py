@@ -115,7 +115,7 @@ def main():
     rep_metrics(tag, out, "hbm", "head, encoder and compaction kernels")
     if traffic:
         from npe_pfn_b200 import build as b
-        json.dump({"dram_bytes_per_launch": traffic, "rows_per_launch": 16384, "srchash": b._source_hash(),
+        json.dump({"dram_bytes_per_launch": traffic, "rows_per_launch": 16384, "srchash": b.files_hash(b.ATTN_KERNEL_FILES), "hashed_files": b.ATTN_KERNEL_FILES,
                    "source": f"profiles/{out}_ncu_attn_tc_metrics.txt (dram__bytes_read.sum + dram__bytes_write.sum of one launch)"},
                   open(os.path.join(ROOT, "profiles", f"{out}_attn_traffic.json"), "w"), indent=1)
         print("attention DRAM bytes per launch:", traffic)
