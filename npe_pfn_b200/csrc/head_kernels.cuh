@@ -1,7 +1,7 @@
 // Bar-distribution head, round-2 kernels (same arithmetic spec as oracle/bar_head.c and head_kernel in small_kernels.cuh,
 // hence the same bits: bucket masses are integers, so every partition of the prefix sums gives the same bucket).
 //
-//  head_row_kernel   one CTA (4 warps) per logits row, the row lives in REGISTERS (10 coalesced float4 loads per
+//  head_row_kernel   one CTA (8 warps) per logits row, the row lives in REGISTERS (5 coalesced float4 loads per
 //                    thread, 20 000 B read exactly once, no shared-memory staging: head_kernel staged 20 KB per warp and
 //                    ran 8 warps per SM at 10 % of the HBM peak).  exp_det + quantisation once per element; 128-element
 //                    block totals by two REDUX (20-bit halves of the 40-bit masses) instead of shuffle trees; only the
@@ -15,7 +15,10 @@
 
 namespace pfn {
 
-constexpr int HR_THREADS = 128, HR_VEC = 10, HR_MAX_B = HR_THREADS * HR_VEC * 4;  // 5120 buckets
+#ifndef PFN_HEAD_THREADS
+#define PFN_HEAD_THREADS 256
+#endif
+constexpr int HR_THREADS = PFN_HEAD_THREADS, HR_WARPS = HR_THREADS / 32, HR_VEC = 5120 / (HR_THREADS * 4), HR_MAX_B = HR_THREADS * HR_VEC * 4;  // 5120 buckets
 
 __device__ __forceinline__ int float_ordered(float f) {  // monotone float -> int map (for REDUX max)
     const int i = __float_as_int(f);
@@ -40,9 +43,9 @@ __device__ __forceinline__ unsigned long long warp_sum_q(unsigned long long s) {
 }
 
 template <bool SAMPLE>
-__global__ void __launch_bounds__(HR_THREADS) head_row_kernel(HeadArgs a) {
-    __shared__ int s_max[4];
-    __shared__ unsigned long long s_w[4];
+__global__ void __launch_bounds__(HR_THREADS, 1024 / HR_THREADS) head_row_kernel(HeadArgs a) {
+    __shared__ int s_max[HR_WARPS];
+    __shared__ unsigned long long s_w[HR_WARPS];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = a.B;
     const int nvec = B >> 2;  // B % 4 == 0
@@ -50,7 +53,7 @@ __global__ void __launch_bounds__(HR_THREADS) head_row_kernel(HeadArgs a) {
     for (int64_t r = blockIdx.x; r < a.M; r += gridDim.x) {
         const float* lg = a.logits + (r / a.group) * a.ld_logits;
         const float4* lg4 = reinterpret_cast<const float4*>(lg);
-        // element order: warp w owns float4 indices [320 w, 320 w + 320), block k of the warp = indices 320 w + 32 k + lane
+        // element order: warp w owns float4 indices [32 HR_VEC w, 32 HR_VEC (w + 1)), block k of the warp = indices 32 HR_VEC w + 32 k + lane
         float v[4 * HR_VEC];
         float mx = -INFINITY;
 #pragma unroll
@@ -65,7 +68,10 @@ __global__ void __launch_bounds__(HR_THREADS) head_row_kernel(HeadArgs a) {
         __syncthreads();  // previous row's readers of s_max / s_w are done
         if (lane == 0) s_max[warp] = wmx;
         __syncthreads();
-        const float m = ordered_float(max(max(s_max[0], s_max[1]), max(s_max[2], s_max[3])));
+        int mi = s_max[0];
+#pragma unroll
+        for (int w = 1; w < HR_WARPS; ++w) mi = max(mi, s_max[w]);
+        const float m = ordered_float(mi);
         // block totals T[k] (uniform across the warp) and the warp total
         unsigned long long T[HR_VEC], wsum = 0ull;
 #pragma unroll
@@ -80,8 +86,9 @@ __global__ void __launch_bounds__(HR_THREADS) head_row_kernel(HeadArgs a) {
         }
         if (lane == 0) s_w[warp] = wsum;
         __syncthreads();
-        const unsigned long long W0 = s_w[0], W1 = s_w[1], W2 = s_w[2], W3 = s_w[3];
-        const unsigned long long Z = W0 + W1 + W2 + W3;
+        unsigned long long Z = 0ull;
+#pragma unroll
+        for (int w = 0; w < HR_WARPS; ++w) Z += s_w[w];
 
         if (!SAMPLE) {
             if (threadIdx.x == 0) {
@@ -107,14 +114,18 @@ __global__ void __launch_bounds__(HR_THREADS) head_row_kernel(HeadArgs a) {
         }
         const double target = (double)u * (double)Z;
         // the warp that holds the target: first w whose inclusive total is not below it
-        const unsigned long long c0 = W0, c1 = c0 + W1, c2 = c1 + W2;
-        int wsel = 4;
+        int wsel = HR_WARPS;
         unsigned long long run = 0ull;
-        if (!((double)c0 < target)) { wsel = 0; run = 0ull; }
-        else if (!((double)c1 < target)) { wsel = 1; run = c0; }
-        else if (!((double)c2 < target)) { wsel = 2; run = c1; }
-        else if (!((double)Z < target)) { wsel = 3; run = c2; }
-        if (wsel == 4) {  // unreachable for u < 1 (spec: last bucket, no mass)
+        {
+            unsigned long long c = 0ull;
+#pragma unroll
+            for (int w = 0; w < HR_WARPS; ++w) {
+                const unsigned long long cw = c + s_w[w];
+                if (wsel == HR_WARPS && !((double)cw < target)) { wsel = w; run = c; }
+                c = cw;
+            }
+        }
+        if (wsel == HR_WARPS) {  // unreachable for u < 1 (spec: last bucket, no mass)
             if (threadIdx.x == 0) {
                 const int idx = B - 1;
                 a.out_theta[r * a.ld_theta] = a.borders[idx];
