@@ -448,6 +448,21 @@ def main():
                "tflops": lp_flops / (lp_ms * 1e-3) / 1e12, "frac_of_peak": lp_flops / (lp_ms * 1e-3) / 1e12 / peak,
                "attn_tflops": tflops(ktl["attn_test"]), "attn_frac_of_peak": tflops(ktl["attn_test"]) / peak}
 
+    # ---- the reference arm's own step on this arm: REF_M draws per call, caches rebuilt, host tensors in and out ------------
+    def step_ref_point():
+        post.append_simulations(theta_p, x_p)
+        return post.sample((REF_M,), xo_p, max_sampling_batch_size=REF_M)
+    step_ref_point()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        step_ref_point()
+    torch.cuda.synchronize()
+    ref_point = {"workload": f"the --impl reference arm's step on the GPU path: {REF_M} draws per call and rank, K/V caches rebuilt "
+                             "every call, host tensors in and out (like for like with the reference arm's value)",
+                 "samples_per_step": REF_M, "value": REF_M * 5 / (time.perf_counter() - t0), "unit": "samples/s"}
+    barrier()
+
     # ---- the other BASELINE.json workloads -------------------------------------------------------------------------------
     configs = None
     if not args.no_configs:
@@ -480,7 +495,7 @@ def main():
                                          "all-gathered over NCCL" if world > 1 else "")},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
-            "logprob": logprob, "configs": configs,
+            "logprob": logprob, "configs": configs, "reference_config_point": ref_point,
         }))
     if world > 1:
         dist.destroy_process_group()
