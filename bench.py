@@ -473,7 +473,7 @@ def main():
 
     if rank == 0:
         cpu = None
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # reported on rank 0 at N = 1 only (the other ranks would idle for minutes)
             try:
                 cpu = cpu_baseline_record(cpu_step_gaussian_linear())
                 cpu["two_moons_full"] = cpu_two_moons_full()
