@@ -86,7 +86,8 @@ struct pfn_ctx {
     float* hd_max = nullptr;
     double* hd_logZ = nullptr;
     int64_t hd_rows = 0;
-    int head_impl = 1;  // 0 = round-1 warp-per-row kernel (shared-memory staging), 1 = register-resident rows + shared-row CDFs
+    int head_impl = 2;  // 0 = round-1 warp-per-row kernel (shared-memory staging), 1 = register-resident rows + shared-row CDFs,
+                        // 2 = 1 with the next row prefetched by a bulk copy and the 15-instruction bucket mass (head_row2_kernel)
     unsigned long long* cp_state = nullptr;  // [cp_cap] look-back tile states | 2 ticket words (zeroed per launch)
     int64_t cp_cap = 0;
     // on-device rejection loop (pfn_sample_rejection): joint test matrix / log-probs of one proposal round
@@ -393,7 +394,7 @@ int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
     // algorithmic bytes: every distinct logits row once (20 000 B) + the row's scalar inputs / outputs
     const int64_t distinct = h.ld_logits == 0 ? 1 : ceil_div(h.M, h.group);
     TimeScope ts(c, st, KC_HEAD, 0.0, (double)distinct * h.B * 4.0 + (double)h.M * 12.0);
-    if (c->head_impl == 1 && h.M >= 2 * distinct && h.M >= 64) {
+    if (c->head_impl >= 1 && h.M >= 2 * distinct && h.M >= 64) {
         // many draws / targets per logits row: CDF once per distinct row, then one thread per draw
         if (distinct > c->hd_rows) {
             PFN_CUDA_OK(cudaStreamSynchronize(st));
@@ -416,7 +417,14 @@ int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
     }
     const bool vec_ok = h.B % 4 == 0 && h.B <= HR_MAX_B && h.ld_logits % 4 == 0 &&
                         (reinterpret_cast<uintptr_t>(h.logits) & 15) == 0;
-    if (c->head_impl == 1 && vec_ok) {
+    if (c->head_impl == 2 && vec_ok) {  // persistent CTAs, next row prefetched by a bulk copy (4 x 20.6 KB of shared memory per SM)
+        const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * HR2_CTAS_PER_SM);
+        if (sample) head_row2_kernel<true><<<blocks, HR_THREADS, 0, st>>>(h);
+        else head_row2_kernel<false><<<blocks, HR_THREADS, 0, st>>>(h);
+        PFN_LAUNCH_OK(c);
+        return 0;
+    }
+    if (c->head_impl >= 1 && vec_ok) {
         const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * 16);
         if (sample) head_row_kernel<true><<<blocks, HR_THREADS, 0, st>>>(h);
         else head_row_kernel<false><<<blocks, HR_THREADS, 0, st>>>(h);

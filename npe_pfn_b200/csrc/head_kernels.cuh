@@ -205,6 +205,206 @@ __global__ void __launch_bounds__(HR_THREADS, 1024 / HR_THREADS) head_row_kernel
     }
 }
 
+// ---- round-2 second generation: the same row kernel with (a) the NEXT row prefetched by one bulk copy (TMA,
+// `cp.async.bulk` + mbarrier) into a 20 KB shared-memory landing buffer while the current row is processed in registers,
+// persistent CTAs (4 per SM); (b) the bucket mass in 15 instructions instead of 28, with the SAME bits as the specification
+// in oracle/bar_head.c (tools/head_arith_check.c walks every fp32 argument in [-64, 0]):
+//   floor(x)           x <= 0, x >= -93:  tr = RD(x + (1.5 * 2^23 + 40)) is exactly 1.5 * 2^23 + 40 + floor(x) (ulp = 1 in
+//                      [2^23, 2^24)), so n = tr - magic is floorf(x) as a float and the low bits of tr are n + 40 as an integer
+//                      (FRND + F2I -> FADD.RM + FADD);
+//   p * 2^n * 2^40     p in [1, 2] and n + 40 + 127 > 0: multiplying by a power of two only moves the exponent field, i.e.
+//                      bits(e * 2^40) = bits(p) + (tr_bits << 23)   (the magic's own low 9 bits are zero);
+//   trunc(e * 2^40)    one F2I.U64.TRUNC of that fp32 value (< 2^42) instead of mantissa / exponent shifts.
+__device__ __forceinline__ unsigned long long mass_q40(float v, float m) {
+    const float t = fmaxf(__fsub_rn(v, m), -64.0f);  // NaN -> -64 like the specification's `!(t > -64)`
+    const float x = __fmul_rn(t, 0x1.715476p+0f);
+    const float kMagic = 12582912.0f + 40.0f;
+    const float tr = __fadd_rd(x, kMagic);
+    const float n = __fsub_rn(tr, kMagic);
+    const float f = __fsub_rn(x, n);
+    float p = 0x1.ca8f0ap-13f;
+    p = __fmaf_rn(p, f, 0x1.44d4d2p-10f);
+    p = __fmaf_rn(p, f, 0x1.3d54d8p-7f);
+    p = __fmaf_rn(p, f, 0x1.c67f50p-5f);
+    p = __fmaf_rn(p, f, 0x1.ebfdf2p-3f);
+    p = __fmaf_rn(p, f, 0x1.62e428p-1f);
+    p = __fmaf_rn(p, f, 0x1.000000p+0f);
+    return __float2ull_rz(__uint_as_float(__float_as_uint(p) + (__float_as_uint(tr) << 23)));
+}
+
+__device__ __forceinline__ void bulk_load_row(uint32_t dst, const float* src, uint32_t bytes, uint32_t bar) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void head_bar_wait(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "HB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra HB_DONE;\n\t"
+        "bra HB_WAIT;\n\t"
+        "HB_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+
+constexpr int HR2_CTAS_PER_SM = 1024 / HR_THREADS;
+
+// Comparisons of the specification are `(double)C < target` with target = (double)u * (double)Z.  C is an integer below
+// 2^53, so C < target  <=>  C < ceil(target): every search below compares integers against tceil = (u64)ceil(target).
+template <bool SAMPLE>
+__global__ void __launch_bounds__(HR_THREADS, HR2_CTAS_PER_SM) head_row2_kernel(HeadArgs a) {
+    __shared__ __align__(128) float s_row[HR_MAX_B];  // landing buffer of the bulk copy: the row AFTER the one in registers
+    __shared__ __align__(8) unsigned long long s_bar;
+    __shared__ __align__(16) int s_max[2][HR_WARPS];                 // double-buffered by row parity: two barriers per row
+    __shared__ __align__(16) unsigned long long s_w[2][HR_WARPS];
+    __shared__ float s_u[2];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int B = a.B;
+    const uint32_t row_bytes = (uint32_t)B * 4u, bar = smem_u32(&s_bar), dst = smem_u32(s_row);
+    const double kLn2x40 = 40.0 * 0.6931471805599453;
+    const bool grouped = a.group != 1;  // 64-bit division only when draws share logits rows
+    const int64_t stride = gridDim.x;
+    // the copy fills s_row[0, B); the tail stays -inf for the whole kernel, so loads and masses need no bounds checks
+    // (exp_det clamps -inf to its floor, whose mass is 0)
+    for (int i = B + (int)threadIdx.x; i < HR_MAX_B; i += HR_THREADS) s_row[i] = -INFINITY;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        const int64_t r0 = blockIdx.x;
+        if (r0 < a.M) bulk_load_row(dst, a.logits + (grouped ? r0 / a.group : r0) * a.ld_logits, row_bytes, bar);
+    }
+    __syncthreads();
+    uint32_t phase = 0;
+    int par = 0;
+    const float4* s4 = reinterpret_cast<const float4*>(s_row) + warp * (32 * HR_VEC) + lane;
+    for (int64_t r = blockIdx.x; r < a.M; r += stride, par ^= 1) {
+        // in the shadow of the copy: address of the next row (thread 0) and this row's uniform (warp 0; Philox is ~90
+        // instructions, so the other seven warps read it from shared memory after the first barrier)
+        const float* next = nullptr;
+        if (threadIdx.x == 0 && r + stride < a.M) next = a.logits + (grouped ? (r + stride) / a.group : r + stride) * a.ld_logits;
+        if (SAMPLE && warp == 0) {
+            float u0;
+            if (a.uniforms) u0 = a.uniforms[r];
+            else {
+                uint32_t c[4];
+                philox4x32_10(a.seed, a.row0 + (uint64_t)r, a.offset, c);
+                u0 = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;
+            }
+            if (lane == 0) s_u[par] = u0;
+        }
+        head_bar_wait(bar, phase);
+        phase ^= 1u;
+        // element order: warp w owns float4 indices [32 HR_VEC w, 32 HR_VEC (w + 1)), block k of the warp = indices 32 HR_VEC w + 32 k + lane
+        float v[4 * HR_VEC];
+        float mx = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < HR_VEC; ++k) {
+            const float4 x = s4[k * 32];
+            v[4 * k] = x.x; v[4 * k + 1] = x.y; v[4 * k + 2] = x.z; v[4 * k + 3] = x.w;
+            mx = fmaxf(mx, fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w)));
+        }
+        const int wmx = __reduce_max_sync(0xffffffffu, float_ordered(mx));
+        if (lane == 0) s_max[par][warp] = wmx;
+        __syncthreads();  // the row has left s_row and the warp maxima are in place
+        if (next) bulk_load_row(dst, next, row_bytes, bar);
+        int mi = s_max[par][0];
+#pragma unroll
+        for (int w = 1; w < HR_WARPS; ++w) mi = max(mi, s_max[par][w]);
+        const float m = ordered_float(mi);
+        unsigned long long sk[HR_VEC], tsum = 0ull;  // this thread's mass per block and in total
+#pragma unroll
+        for (int k = 0; k < HR_VEC; ++k) {
+            sk[k] = mass_q40(v[4 * k], m) + mass_q40(v[4 * k + 1], m) + mass_q40(v[4 * k + 2], m) + mass_q40(v[4 * k + 3], m);
+            tsum += sk[k];
+        }
+        // warp total: tsum < 20 * 2^40 + ..., split at bit 22 so that both 32-lane REDUX sums stay below 2^32
+        const unsigned long long wsum = ((unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)(tsum >> 22)) << 22) +
+                                        (unsigned long long)__reduce_add_sync(0xffffffffu, (unsigned)(tsum & 0x3FFFFFull));
+        if (lane == 0) s_w[par][warp] = wsum;
+        __syncthreads();
+        unsigned long long Z = 0ull, run = 0ull;  // partition sum; mass of the warps before this one
+#pragma unroll
+        for (int w = 0; w < HR_WARPS; ++w) {
+            const unsigned long long x = s_w[par][w];
+            if (w < warp) run += x;
+            Z += x;
+        }
+
+        if (!SAMPLE) {
+            if (threadIdx.x == 0) {
+                const float* lg = a.logits + (grouped ? r / a.group : r) * a.ld_logits;
+                const double logZ = log((double)Z) - kLn2x40;
+                const double logp = bar_logp(lg, B, a.borders, m, logZ, a.y[r * a.ld_y]);
+                if (a.out_nll) a.out_nll[r] = (float)(-logp);
+                if (a.out_logp) {
+                    float lp = (float)logp;
+                    if (lp == -INFINITY) lp = a.log_eps;
+                    a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+                }
+            }
+            continue;
+        }
+
+        const float u = s_u[par];
+        const double target = (double)u * (double)Z;
+        const unsigned long long tceil = (unsigned long long)ceil(target);
+        // this warp holds the target iff its inclusive total is the first one not below it
+        const bool mine = run + wsum >= tceil && (warp == 0 || run < tceil);
+        int idx = -1;
+        double frac = 0.0;
+        if (tceil > Z) {  // unreachable for u < 1 (spec: last bucket, no mass)
+            if (threadIdx.x == 0) idx = B - 1;
+        } else if (mine) {
+            int ksel = HR_VEC - 1;  // block of the warp that holds the target
+            {
+                bool found = false;
+#pragma unroll
+                for (int k = 0; k < HR_VEC; ++k) {
+                    const unsigned long long Tk = warp_sum_q(sk[k]);
+                    if (!found) {
+                        if (run + Tk >= tceil) { ksel = k; found = true; }
+                        else run += Tk;
+                    }
+                }
+            }
+            float lv0 = 0.f, lv1 = 0.f, lv2 = 0.f, lv3 = 0.f;  // this lane's four logits of that block
+            unsigned long long s4q = 0ull;
+#pragma unroll
+            for (int k = 0; k < HR_VEC; ++k)
+                if (k == ksel) { lv0 = v[4 * k]; lv1 = v[4 * k + 1]; lv2 = v[4 * k + 2]; lv3 = v[4 * k + 3]; s4q = sk[k]; }
+            const unsigned long long inc = warp_scan_u64(s4q, lane) + run;  // inclusive prefix up to this lane's last element
+            const int lsel = __popc(__ballot_sync(0xffffffffu, inc < tceil));  // first lane not below the target
+            if (lane == min(lsel, 31)) {
+                const unsigned long long q0 = mass_q40(lv0, m), q1 = mass_q40(lv1, m), q2 = mass_q40(lv2, m), q3 = mass_q40(lv3, m);
+                unsigned long long Cprev = inc - s4q, qsel = q3;
+                int j = 3;
+                if (Cprev + q0 >= tceil) { j = 0; qsel = q0; }
+                else if (Cprev + q0 + q1 >= tceil) { j = 1; qsel = q1; Cprev += q0; }
+                else if (Cprev + q0 + q1 + q2 >= tceil) { j = 2; qsel = q2; Cprev += q0 + q1; }
+                else Cprev += q0 + q1 + q2;
+                idx = 4 * (warp * (32 * HR_VEC) + ksel * 32 + lane) + j;
+                frac = qsel ? (target - (double)Cprev) / (double)qsel : 0.0;
+                frac = fmin(fmax(frac, 0.0), 1.0);
+            }
+        }
+        if (idx >= 0) {  // exactly one thread of the CTA
+            const double lo = (double)a.borders[idx], hi = (double)a.borders[idx + 1];
+            const float th = (float)(lo + (hi - lo) * frac);
+            a.out_theta[r * a.ld_theta] = th;
+            if (a.out_bin) a.out_bin[r] = idx;
+            if (a.out_u) a.out_u[r] = u;
+            if (a.out_logp) {
+                const float* lg = a.logits + (grouped ? r / a.group : r) * a.ld_logits;
+                const double logZ = log((double)Z) - kLn2x40;
+                float lp = (float)bar_logp(lg, B, a.borders, m, logZ, th);
+                if (lp == -INFINITY) lp = a.log_eps;
+                a.out_logp[r] = a.accumulate ? a.out_logp[r] + lp : lp;
+            }
+        }
+    }
+}
+
 // ---- shared logits rows: integer CDF once per distinct row, then one thread per draw / target ---------------------------
 struct HeadCdf {            // per distinct logits row
     unsigned long long* cdf;  // [rows][B] inclusive prefix sums of the bucket masses

@@ -345,16 +345,31 @@ def test_edge_cases_round2(engine, weights):
     y = torch.linspace(float(borders[0]) - 1, float(borders[-1]) + 1, 500)
     nll = engine.head_nll(2, logits[:1], y).cpu()
     assert torch.allclose(nll, bar_head.nll(logits[:1].expand(500, B).contiguous(), borders, y), atol=2e-5, rtol=1e-5)
-    # old head kernel (head_impl = 0) gives the same bits as the new ones
-    u = torch.rand(300, generator=g)
-    lg = torch.randn(300, B, generator=g)
-    a = engine.head_sample(2, lg, uniforms=u, return_bins=True)
-    engine.set_option("head_impl", 0)
+    # the three generations of the head kernel (0 = round 1 warp per row, 1 = register-resident row, 2 = default: bulk-copy
+    # prefetch + 15-instruction bucket mass) give the same bits; rows with -inf / NaN / very sharp logits included, and more
+    # rows than resident CTAs so that the persistent kernel's prefetch ring wraps
+    n_rows = 148 * 4 * 3 + 77
+    u = torch.rand(n_rows, generator=g)
+    lg = torch.randn(n_rows, B, generator=g)
+    lg[1] *= 40.0
+    lg[2, ::3] = float("-inf")
+    lg[3, 100:200] = float("nan")
+    lg[4] = 0.0
+    lg[5, :] = -1e4; lg[5, 4321] = 3.0
+    a = engine.head_sample(2, lg, uniforms=u, return_bins=True, with_log_prob=True)
+    th_ref, idx_ref, _ = bar_head.sample(lg, borders, uniforms=u)
+    assert torch.equal(a[1].cpu(), idx_ref) and torch.equal(a[0].cpu(), th_ref)
+    y_t = torch.randn(n_rows, generator=g)
+    y_t[3] = float(borders[2500])  # keep the target of the NaN row off its NaN buckets (NaN != NaN under torch.equal)
+    nll_a = engine.head_nll(2, lg, y_t)
     try:
-        b = engine.head_sample(2, lg, uniforms=u, return_bins=True)
+        for impl in (0, 1):
+            engine.set_option("head_impl", impl)
+            b = engine.head_sample(2, lg, uniforms=u, return_bins=True, with_log_prob=True)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), impl
+            assert torch.equal(nll_a, engine.head_nll(2, lg, y_t)), impl
     finally:
-        engine.set_option("head_impl", 1)
-    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+        engine.set_option("head_impl", 2)
     # uniform box proposals: inside the box, reproducible, different rows differ
     lo, hi = torch.tensor([-1.0, 2.0, 0.0, -5.0, 1.0]), torch.tensor([1.0, 3.0, 10.0, -4.0, 1.5])
     c1 = engine.uniform_box(lo, hi, 1000, seed=9, row0=5)
