@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(HR_THREADS, HR2_CTAS_PER_SM) head_row2_kernel(
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ __align__(16) int s_max[2][HR_WARPS];                 // double-buffered by row parity: two barriers per row
     __shared__ __align__(16) unsigned long long s_w[2][HR_WARPS];
-    __shared__ float s_u[2];
+    __shared__ float s_u[HR_THREADS];  // uniforms of this CTA's next HR_THREADS rows
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int B = a.B;
     const uint32_t row_bytes = (uint32_t)B * 4u, bar = smem_u32(&s_bar), dst = smem_u32(s_row);
@@ -278,20 +278,26 @@ __global__ void __launch_bounds__(HR_THREADS, HR2_CTAS_PER_SM) head_row2_kernel(
     uint32_t phase = 0;
     int par = 0;
     const float4* s4 = reinterpret_cast<const float4*>(s_row) + warp * (32 * HR_VEC) + lane;
-    for (int64_t r = blockIdx.x; r < a.M; r += stride, par ^= 1) {
-        // in the shadow of the copy: address of the next row (thread 0) and this row's uniform (warp 0; Philox is ~90
-        // instructions, so the other seven warps read it from shared memory after the first barrier)
+    int it = 0;
+    for (int64_t r = blockIdx.x; r < a.M; r += stride, par ^= 1, ++it) {
+        // in the shadow of the copy: address of the next row (thread 0); every HR_THREADS rows of this CTA, one uniform per
+        // thread for the next HR_THREADS rows (Philox is ~90 instructions: once per thread instead of once per warp and row,
+        // and no warp arrives late at the first barrier because of it)
         const float* next = nullptr;
         if (threadIdx.x == 0 && r + stride < a.M) next = a.logits + (grouped ? (r + stride) / a.group : r + stride) * a.ld_logits;
-        if (SAMPLE && warp == 0) {
-            float u0;
-            if (a.uniforms) u0 = a.uniforms[r];
-            else {
-                uint32_t c[4];
-                philox4x32_10(a.seed, a.row0 + (uint64_t)r, a.offset, c);
-                u0 = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;
+        if (SAMPLE && (it & (HR_THREADS - 1)) == 0) {
+            __syncthreads();  // readers of the previous batch are done
+            const int64_t rr = r + (int64_t)threadIdx.x * stride;
+            float u0 = 0.f;
+            if (rr < a.M) {
+                if (a.uniforms) u0 = a.uniforms[rr];
+                else {
+                    uint32_t c[4];
+                    philox4x32_10(a.seed, a.row0 + (uint64_t)rr, a.offset, c);
+                    u0 = ((float)(c[0] >> 9) + 0.5f) * 0x1.0p-23f;
+                }
             }
-            if (lane == 0) s_u[par] = u0;
+            s_u[threadIdx.x] = u0;  // published by the first barrier below
         }
         head_bar_wait(bar, phase);
         phase ^= 1u;
@@ -346,9 +352,9 @@ __global__ void __launch_bounds__(HR_THREADS, HR2_CTAS_PER_SM) head_row2_kernel(
             continue;
         }
 
-        const float u = s_u[par];
+        const float u = s_u[it & (HR_THREADS - 1)];
         const double target = (double)u * (double)Z;
-        const unsigned long long tceil = (unsigned long long)ceil(target);
+        const unsigned long long tceil = __double2ull_ru(target);  // target >= 0
         // this warp holds the target iff its inclusive total is the first one not below it
         const bool mine = run + wsum >= tceil && (warp == 0 || run < tceil);
         int idx = -1;

@@ -350,6 +350,7 @@ def test_edge_cases_round2(engine, weights):
     # rows than resident CTAs so that the persistent kernel's prefetch ring wraps
     n_rows = 148 * 4 * 3 + 77
     u = torch.rand(n_rows, generator=g)
+    u[0], u[7] = 0.0, 1.0 - 2.0 ** -24  # both ends of what torch.rand can return
     lg = torch.randn(n_rows, B, generator=g)
     lg[1] *= 40.0
     lg[2, ::3] = float("-inf")
@@ -368,6 +369,16 @@ def test_edge_cases_round2(engine, weights):
             b = engine.head_sample(2, lg, uniforms=u, return_bins=True, with_log_prob=True)
             assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), impl
             assert torch.equal(nll_a, engine.head_nll(2, lg, y_t)), impl
+        # more than 256 rows per persistent CTA (the per-CTA batch of Philox uniforms wraps), Philox uniforms, on the device
+        big = 148 * 4 * 256 + 1000
+        lg_big = torch.randn(big, B, device="cuda")
+        engine.set_option("head_impl", 1)
+        ref = engine.head_sample(2, lg_big, seed=77, row0=123456789, offset=3, return_bins=True)
+        engine.set_option("head_impl", 2)
+        got = engine.head_sample(2, lg_big, seed=77, row0=123456789, offset=3, return_bins=True)
+        assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
+        assert got[1].float().std() > 100  # not degenerate
+        del lg_big
     finally:
         engine.set_option("head_impl", 2)
     # uniform box proposals: inside the box, reproducible, different rows differ
