@@ -112,7 +112,8 @@ def main():
     launch_summary(tag, out)
     traffic = rep_metrics(tag, out, "attn_tc", "item attention of test rows, one launch: 16384 rows x 6 heads x T columns, N = 10000 keys")
     rep_metrics(tag, out, "gemm_tc", "five consecutive projection / fused-MLP launches")
-    rep_metrics(tag, out, "hbm", "head, encoder and compaction kernels")
+    rep_metrics(tag, out, "hbm", "encoder, K/V cache writer and compaction kernels")
+    rep_metrics(tag, out, "head", "head_row2_kernel: two launches of 16 384 logits rows x 5000 buckets")
     if traffic:
         from npe_pfn_b200 import build as b
         json.dump({"dram_bytes_per_launch": traffic, "rows_per_launch": 16384, "srchash": b.files_hash(b.ATTN_KERNEL_FILES), "hashed_files": b.ATTN_KERNEL_FILES,
