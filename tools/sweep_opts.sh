@@ -14,7 +14,7 @@ for line in open(sys.argv[1]):
     if line.startswith("{"):
         d = json.loads(line); r = d["roofline"]; ok = True
         print(f"{sys.argv[2]:40s} value {d['value']:8.0f}  attn_test {r['per_class_tflops']['attn_test']:6.1f} TF  attn_ctx {r['per_class_tflops']['attn_ctx']:6.1f} TF  "
-              f"ms/step {d['ms_per_step']:7.1f}  sm {d['clocks']['sm_mhz']}")
+              f"ms/step {d['ms_per_step']:7.1f}  gemm {r['per_class_ms']['gemm']:6.1f} ms  mlp {r['per_class_ms']['mlp']:5.1f} ms  sm {d['clocks']['sm_mhz']}")
 if not ok:
     print(sys.argv[2], "FAILED"); print(open(sys.argv[1]).read()[-800:])
 P
