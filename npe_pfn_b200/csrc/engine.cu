@@ -88,6 +88,7 @@ struct pfn_ctx {
     int64_t hd_rows = 0;
     int head_impl = 2;  // 0 = round-1 warp-per-row kernel (shared-memory staging), 1 = register-resident rows + shared-row CDFs,
                         // 2 = 1 with the next row prefetched by a bulk copy and the 15-instruction bucket mass (head_row2_kernel)
+    int head_threads = 128;  // threads per logits row of head_row2_kernel (256: 4 CTAs per SM, 2.97 TB/s; 128: 5 CTAs per SM, 3.31 TB/s; 64: 6 CTAs per SM)
     unsigned long long* cp_state = nullptr;  // [cp_cap] look-back tile states | 2 ticket words (zeroed per launch)
     int64_t cp_cap = 0;
     // on-device rejection loop (pfn_sample_rejection): joint test matrix / log-probs of one proposal round
@@ -418,9 +419,19 @@ int launch_head(pfn_ctx* c, const HeadArgs& h, bool sample, cudaStream_t st) {
     const bool vec_ok = h.B % 4 == 0 && h.B <= HR_MAX_B && h.ld_logits % 4 == 0 &&
                         (reinterpret_cast<uintptr_t>(h.logits) & 15) == 0;
     if (c->head_impl == 2 && vec_ok) {  // persistent CTAs, next row prefetched by a bulk copy (4 x 20.6 KB of shared memory per SM)
-        const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * HR2_CTAS_PER_SM);
-        if (sample) head_row2_kernel<true><<<blocks, HR_THREADS, 0, st>>>(h);
-        else head_row2_kernel<false><<<blocks, HR_THREADS, 0, st>>>(h);
+        if (c->head_threads == 64) {
+            const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * 6);
+            if (sample) head_row2_kernel<true, 64, 6><<<blocks, 64, 0, st>>>(h);
+            else head_row2_kernel<false, 64, 6><<<blocks, 64, 0, st>>>(h);
+        } else if (c->head_threads == 128) {
+            const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * 5);
+            if (sample) head_row2_kernel<true, 128, 5><<<blocks, 128, 0, st>>>(h);
+            else head_row2_kernel<false, 128, 5><<<blocks, 128, 0, st>>>(h);
+        } else {
+            const unsigned blocks = (unsigned)std::min<int64_t>(h.M, (int64_t)c->num_sms * 4);
+            if (sample) head_row2_kernel<true, 256, 4><<<blocks, 256, 0, st>>>(h);
+            else head_row2_kernel<false, 256, 4><<<blocks, 256, 0, st>>>(h);
+        }
         PFN_LAUNCH_OK(c);
         return 0;
     }
@@ -560,6 +571,11 @@ int pfn_set_option(pfn_ctx* c, const char* key, int64_t value) {
     if (!strcmp(key, "attn_lean")) { c->attn_lean = (int)value; return 0; }
     if (!strcmp(key, "mlp_fused")) { c->mlp_fused = (int)value; return 0; }
     if (!strcmp(key, "head_impl")) { c->head_impl = (int)value; return 0; }
+    if (!strcmp(key, "head_threads")) {
+        PFN_REQUIRE(value == 64 || value == 128 || value == 256, "head_threads must be 64, 128 or 256");
+        c->head_threads = (int)value;
+        return 0;
+    }
     if (!strcmp(key, "feat_fused")) { c->feat_fused = (int)value; return 0; }
     if (!strcmp(key, "dec_rows")) {  // rows per decoder + head pass (logits workspace = dec_rows x num_buckets fp32)
         PFN_REQUIRE(value >= 128 && value <= (1 << 20), "dec_rows out of range");

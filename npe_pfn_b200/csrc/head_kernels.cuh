@@ -247,12 +247,15 @@ __device__ __forceinline__ void head_bar_wait(uint32_t bar, uint32_t parity) {
         "HB_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
 
-constexpr int HR2_CTAS_PER_SM = 1024 / HR_THREADS;
 
 // Comparisons of the specification are `(double)C < target` with target = (double)u * (double)Z.  C is an integer below
 // 2^53, so C < target  <=>  C < ceil(target): every search below compares integers against tceil = (u64)ceil(target).
-template <bool SAMPLE>
-__global__ void __launch_bounds__(HR_THREADS, HR2_CTAS_PER_SM) head_row2_kernel(HeadArgs a) {
+// THREADS per logits row (a CTA), CTAS resident per SM: <256, 4> = 5 float4 per thread, 64 registers; <128, 5> = 10 float4 per
+// thread (twice the independent work per warp, half the per-warp bookkeeping per row, four instead of eight warps per barrier).
+template <bool SAMPLE, int THREADS, int CTAS>
+__global__ void __launch_bounds__(THREADS, CTAS) head_row2_kernel(HeadArgs a) {
+    constexpr int HR_THREADS = THREADS, HR_WARPS = THREADS / 32, HR_VEC = 5120 / (THREADS * 4);
+    static_assert(HR_VEC * THREADS * 4 == HR_MAX_B && (THREADS & (THREADS - 1)) == 0, "threads per row must divide 1280 float4 evenly");
     __shared__ __align__(128) float s_row[HR_MAX_B];  // landing buffer of the bulk copy: the row AFTER the one in registers
     __shared__ __align__(8) unsigned long long s_bar;
     __shared__ __align__(16) int s_max[2][HR_WARPS];                 // double-buffered by row parity: two barriers per row

@@ -346,7 +346,7 @@ def test_edge_cases_round2(engine, weights):
     nll = engine.head_nll(2, logits[:1], y).cpu()
     assert torch.allclose(nll, bar_head.nll(logits[:1].expand(500, B).contiguous(), borders, y), atol=2e-5, rtol=1e-5)
     # the three generations of the head kernel (0 = round 1 warp per row, 1 = register-resident row, 2 = default: bulk-copy
-    # prefetch + 15-instruction bucket mass) give the same bits; rows with -inf / NaN / very sharp logits included, and more
+    # prefetch + 15-instruction bucket mass, 64 / 128 / 256 threads per row) give the same bits; rows with -inf / NaN / very sharp logits included, and more
     # rows than resident CTAs so that the persistent kernel's prefetch ring wraps
     n_rows = 148 * 4 * 3 + 77
     u = torch.rand(n_rows, generator=g)
@@ -369,6 +369,14 @@ def test_edge_cases_round2(engine, weights):
             b = engine.head_sample(2, lg, uniforms=u, return_bins=True, with_log_prob=True)
             assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), impl
             assert torch.equal(nll_a, engine.head_nll(2, lg, y_t)), impl
+        # 128 threads per row (5 CTAs per SM) instead of 256
+        engine.set_option("head_impl", 2)
+        for threads in (64, 256):  # the default is 128 threads per row (5 CTAs per SM)
+            engine.set_option("head_threads", threads)
+            b = engine.head_sample(2, lg, uniforms=u, return_bins=True, with_log_prob=True)
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), threads
+            assert torch.equal(nll_a, engine.head_nll(2, lg, y_t)), threads
+        engine.set_option("head_threads", 128)
         # more than 256 rows per persistent CTA (the per-CTA batch of Philox uniforms wraps), Philox uniforms, on the device
         big = 148 * 4 * 256 + 1000
         lg_big = torch.randn(big, B, device="cuda")
@@ -377,10 +385,16 @@ def test_edge_cases_round2(engine, weights):
         engine.set_option("head_impl", 2)
         got = engine.head_sample(2, lg_big, seed=77, row0=123456789, offset=3, return_bins=True)
         assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1])
+        for threads in (64, 256):
+            engine.set_option("head_threads", threads)
+            got = engine.head_sample(2, lg_big, seed=77, row0=123456789, offset=3, return_bins=True)
+            assert torch.equal(ref[0], got[0]) and torch.equal(ref[1], got[1]), threads
+        engine.set_option("head_threads", 128)
         assert got[1].float().std() > 100  # not degenerate
         del lg_big
     finally:
         engine.set_option("head_impl", 2)
+        engine.set_option("head_threads", 128)
     # uniform box proposals: inside the box, reproducible, different rows differ
     lo, hi = torch.tensor([-1.0, 2.0, 0.0, -5.0, 1.0]), torch.tensor([1.0, 3.0, 10.0, -4.0, 1.5])
     c1 = engine.uniform_box(lo, hi, 1000, seed=9, row0=5)
