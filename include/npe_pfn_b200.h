@@ -68,7 +68,11 @@ int pfn_ctx_destroy(pfn_ctx* ctx);
  * tiles per CTA; measured slower than 1, kept as a parity-tested opt-in); "mlp_fused" 1 (default) = MLP sub-layer in one kernel (hidden activation stays on chip), 0 = two GEMM launches; "chunk_rows" = test rows per pass; "standardize_y" 0 = targets enter the y-encoder unscaled (classifier head:
  * class indices, npe_pfn.py:610, 661); "attn_poly" k = k of every 16 pairs of softmax exponentials on the FMA pipes; "attn_lean" 2 (default) / 1 = reference maximum folded
  * into the Q K^T MMA + overflow check instead of the maximum pass (1: every reference change redoes / slows the warp's tile, 2: kept on the
- * fast path), 0 = explicit maximum pass per tile; "time_kernels" 1 = record a
+ * fast path), 0 = explicit maximum pass per tile; "head_impl" 2 (default) = head_row2_kernel (persistent CTAs, next logits row
+ * prefetched by a bulk copy, 15-instruction bucket mass), 1 = the same arithmetic without prefetch, 0 = round-1 warp-per-row
+ * kernel (all three bit-identical); "head_threads" 128 (default) / 64 / 256 = threads per logits row of head_row2_kernel;
+ * "dec_rows" = rows per decoder + head pass (default 16 384; logits workspace = dec_rows x num_buckets fp32);
+ * "time_kernels" 1 = record a
  * CUDA event pair around every attention / GEMM launch on its stream (read back with pfn_kernel_times). */
 int pfn_set_option(pfn_ctx* ctx, const char* key, int64_t value);
 
