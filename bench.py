@@ -124,6 +124,20 @@ def flops_per_step(S, dx=DIM_X, dth=DIM_THETA, N=N_CTX, prefill=True, dim0_rows=
     return f
 
 
+def bench_config(S, world):
+    """`config` of the JSON line: the workload both arms are quoted on (the --impl reference arm times a bounded sample
+    of it on the host and says which in `cpu_baseline.sample`)."""
+    return {"workload": "gaussian_linear: 10-D theta / 10-D x, 10k simulations, "
+                        f"{S} posterior draws per GPU per step via the autoregressive sampler",
+            "samples_per_gpu": S, "context_rows": N_CTX, "n_estimators": 1,
+            "weights": "seeded random init of the TabPFNv2 regressor architecture",
+            "prefill_in_step": True, "api": "npe_pfn_b200.distributed.sample_sharded -> NPE_PFN_Core.sample",
+            "l2": "per-step working set (1.3 GB of K/V cache + activations) exceeds the 126 MB L2",
+            "parallelism": f"rows sharded over {world} GPU(s), context replicated"
+                           + ("; per-dimension prefills split over the ranks, slots broadcast over NCCL; draws "
+                              "all-gathered over NCCL" if world > 1 else "")}
+
+
 # ---- clocks ---------------------------------------------------------------------------------------------------------
 class ClockSampler:
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -242,11 +256,12 @@ def run_reference_arm(args):
         "steps": len(steps), "warmup": 0, "requested_steps": args.steps, "requested_warmup": args.warmup,
         "ms_per_step": 1000.0 * dt / len(steps), "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"gaussian_linear: 10-D theta / 10-D x, 10k simulations, {REF_M} posterior draws per step "
-                               "via the reference's autoregressive loop on the host CPU (all 10 dimensions, re-fit per "
-                               "dimension), wall clock; steps bounded by a time budget",
-                   "samples_per_step": REF_M, "context_rows": N_CTX, "n_estimators": 1,
-                   "weights": "seeded random init of the TabPFNv2 regressor architecture"},
+        # the workload the GPU arm is quoted on; what this arm ran of it (a bounded sample) is `sample` / `cpu_baseline.sample`
+        "config": bench_config(args.samples, args.gpus),
+        "sample": f"bounded sample of that workload on the host CPU: {REF_M} posterior draws per step through the reference's "
+                  "autoregressive loop (all 10 dimensions, context of 10 000 simulations re-fitted per dimension), wall "
+                  "clock; number of steps bounded by --ref-budget",
+        "samples_per_step": REF_M,
         "cpu_baseline": rec,
         "e2e": {"value": v, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -484,15 +499,7 @@ def main():
             "metric": METRIC, "value": value, "unit": "samples/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "gaussian_linear: 10-D theta / 10-D x, 10k simulations, "
-                                   f"{S} posterior draws per GPU per step via the autoregressive sampler",
-                       "samples_per_gpu": S, "context_rows": N_CTX, "n_estimators": 1,
-                       "weights": "seeded random init of the TabPFNv2 regressor architecture",
-                       "prefill_in_step": True, "api": "npe_pfn_b200.distributed.sample_sharded -> NPE_PFN_Core.sample",
-                       "l2": "per-step working set (1.3 GB of K/V cache + activations) exceeds the 126 MB L2",
-                       "parallelism": f"rows sharded over {world} GPU(s), context replicated"
-                                      + ("; per-dimension prefills split over the ranks, slots broadcast over NCCL; draws "
-                                         "all-gathered over NCCL" if world > 1 else "")},
+            "config": bench_config(S, world),
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
             "gpu_launches": launches, "clocks": clk, "roofline": roofline, "cpu_baseline": cpu,
             "logprob": logprob, "configs": configs, "reference_config_point": ref_point,
