@@ -211,3 +211,26 @@ def test_fast_bucket_mass_arithmetic_equals_specification(tmp_path):
     out = subprocess.run([exe, "16"], capture_output=True, text=True)
     assert out.returncode == 0, out.stdout + out.stderr
     assert "mismatches 0" in out.stdout and int(out.stdout.split()[1]) > 69_000_000
+
+
+def test_integer_target_comparison_equals_specification():
+    """head_row2_kernel replaces every `(double)C < target` of the specification (oracle/bar_head.c:116, target =
+    (double)u * (double)Z) by the integer comparison `C < ceil(target)`.  Equivalent for every integer C below 2^53:
+    checked here in exact arithmetic around the target for random partition sums Z and fp32 uniforms u, including u = 0,
+    the largest u torch.rand can return, and targets that are integers themselves."""
+    import random
+    rng = random.Random(5)
+    fr = np.float32
+    us = [0.0, float(fr(2.0 ** -24)), float(fr(1.0 - 2.0 ** -24)), 0.5, 0.25]
+    us += [float(fr(rng.random())) for _ in range(400)]
+    for u in us:
+        for _ in range(25):
+            Z = rng.randrange(1 << 40, 5000 << 40)
+            if rng.random() < 0.2:
+                Z = (Z >> 30) << 30  # make u * Z an integer more often
+            target = float(u) * float(Z)          # double product, as in the kernels (Z < 2^53 is exact as a double)
+            tceil = math.ceil(target)              # exact: Python converts the double to an integer without rounding
+            base = int(target)
+            for C in {0, 1, Z, base - 2, base - 1, base, base + 1, base + 2, tceil - 1, tceil, tceil + 1}:
+                if 0 <= C < (1 << 53):
+                    assert (float(C) < target) == (C < tceil), (u, Z, C)
