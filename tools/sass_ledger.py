@@ -17,7 +17,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "npe_pfn_b200", "_lib", "libnpe_pfn_b200.so")
-KEY = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "MUFU", "FFMA2", "FADD2", "FMNMX3", "HMMA", "REDUX"]
+KEY = ["UTCHMMA", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "MUFU", "FFMA2", "FADD2", "FMNMX3", "HMMA", "REDUX"]
 
 
 def demangle(name):
